@@ -1,0 +1,519 @@
+// ea_gemm.cu — the tcgen05 GEMM / implicit-GEMM convolution kernel (sm_100a).
+//
+// One kernel serves every dense contraction of the UNet / ControlNet / SAM hot path
+// (SURVEY.md §8a rows R1, R7, R9-R12):
+//   * Linear layers and 1x1 convolutions            (mode LINEAR)
+//   * 3x3 stride-1 pad-1 convolutions on NHWC data  (mode CONV_S1), optionally with the
+//     ResBlock's 1x1 skip convolution folded in as extra K-blocks (openaimodel.py:233-240,274)
+//   * 3x3 stride-2 pad-1 convolutions (Downsample, openaimodel.py:133-159) (mode CONV_S2)
+//
+// Structure (one 128 x BN output tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the
+// other's main loop):
+//   warp 0     TMA producer : A tile (128 rows x 64 halves, SWIZZLE_128B) and B tile (BN x 64)
+//                             into a `stages`-deep shared-memory ring, mbarrier-signalled.
+//                             For convolutions the A tile of filter tap (kh,kw) is a 4-D box
+//                             {64ch, bw, bh, bn} of the NHWC tensor shifted by (kh-1, kw-1); the
+//                             zero padding is TMA out-of-bounds fill, no im2col buffer exists.
+//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per
+//                             stage, accumulating fp32 in TMEM; tcgen05.commit releases stages.
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue     : tcgen05.ld the accumulator (thread <-> row), fused
+//                             bias / time-embedding row vector / SiLU|GELU|GEGLU / scale /
+//                             residual add / accumulate-into-destination (ControlNet zero-conv
+//                             residual, cldm/cldm.py:34-41) / dual store, 16-byte stores.
+#include "ea_common.cuh"
+#include "ea_internal.h"
+
+namespace ea {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 256;
+
+struct GemmKParams {
+  int M, N;
+  int mode;
+  int nkb_main;   // K-blocks from the main A source
+  int nkb_extra;  // K-blocks from the extra (1x1 skip) A source
+  int cin_blocks; // Cin / 64 (conv): K-blocks per filter tap
+  int BN, stages;
+  // conv geometry (output space)
+  int H, W, Bsz;
+  int bw, bh, bn;
+  int tiles_w, tiles_h;
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  int rows_per_batch;
+  int rowvec_ld;
+  const ea_half* residual;
+  long long ldr;
+  ea_half* out;
+  long long ldo;
+  ea_half* out2;
+  long long ldo2;
+  float* out_f32;  // optional fp32 output (same ldo) instead of half
+  int act;
+  float out_scale;
+  int accumulate;
+};
+
+__device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n0, int& h0,
+                                            int& w0) {
+  // tiles enumerate (image block, tile row, tile col); an image block is bn images
+  int per_blk = p.tiles_w * p.tiles_h;
+  int nb = tm / per_blk;
+  int r = tm - nb * per_blk;
+  int th = r / p.tiles_w;
+  n0 = nb * p.bn;
+  h0 = th * p.bh;
+  w0 = (r - th * p.tiles_w) * p.bw;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+               const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmB,
+               const GemmKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages] x (A 16 KB | B BN*128 B), then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int a_bytes = BM * BK * 2;
+  const int b_bytes = p.BN * BK * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tm = blockIdx.x;
+  const int tn = blockIdx.y;
+  const int nkb = p.nkb_main + p.nkb_extra;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.mode == EA_GEMM_CONV_S2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmA3);
+    }
+    if (p.nkb_extra > 0) tma_prefetch_desc(&tmAx);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, (uint32_t)(p.BN < 32 ? 32 : p.BN));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int n0 = 0, h0 = 0, w0 = 0;
+      if (p.mode != EA_GEMM_LINEAR) tile_origin(p, tm, n0, h0, w0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        if (p.mode == EA_GEMM_LINEAR) {
+          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, tm * BM);
+        } else if (kb >= p.nkb_main) {
+          // fused 1x1 skip convolution: centre tap of the raw block input
+          int c0 = (kb - p.nkb_main) * BK;
+          tma_load_4d(sa, &tmAx, &full_bar[stage], c0, w0, h0, n0);
+        } else {
+          int tap = kb / p.cin_blocks;
+          int c0 = (kb - tap * p.cin_blocks) * BK;
+          int kh = tap / 3, kw = tap - kh * 3;
+          if (p.mode == EA_GEMM_CONV_S1) {
+            tma_load_4d(sa, &tmA0, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, n0);
+          } else {
+            // stride 2: input row 2*oh + kh - 1 lives in phase ph = (kh != 1) at index oh + dh
+            int ph = (kh == 1) ? 0 : 1, dh = (kh == 0) ? -1 : 0;
+            int pw = (kw == 1) ? 0 : 1, dw = (kw == 0) ? -1 : 0;
+            int sel = ph * 2 + pw;
+            const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
+            tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
+          }
+        }
+        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tn * p.BN);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BM, (uint32_t)p.BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        uint32_t sb = sa + a_bytes;
+        uint64_t da = umma_desc_k_sw128(sa, 1024);
+        uint64_t db = umma_desc_k_sw128(sb, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int wq = warp - 4;             // TMEM lane quarter
+    const int r = wq * 32 + lane;        // tile row owned by this thread
+    long long m;                         // global output row
+    bool row_ok;
+    int batch;
+    if (p.mode == EA_GEMM_LINEAR) {
+      m = (long long)tm * BM + r;
+      row_ok = m < p.M;
+      batch = p.rows_per_batch > 0 ? (int)(m / p.rows_per_batch) : 0;
+    } else {
+      int n0, h0, w0;
+      tile_origin(p, tm, n0, h0, w0);
+      int dn = r / (p.bw * p.bh);
+      int rr = r - dn * (p.bw * p.bh);
+      int dh = rr / p.bw;
+      int dw = rr - dh * p.bw;
+      int n = n0 + dn, h = h0 + dh, w = w0 + dw;
+      row_ok = (n < p.Bsz) && (h < p.H) && (w < p.W);
+      m = ((long long)n * p.H + h) * p.W + w;
+      batch = n;
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int ncol0 = tn * p.BN;
+    if (p.act == EA_ACT_GEGLU) {
+      // tile columns: [0, BN/2) = value half, [BN/2, BN) = gate half (weights pre-interleaved)
+      const int half_bn = p.BN >> 1;
+      for (int c = 0; c < half_bn; c += 32) {
+        uint32_t xv[32], gv[32];
+        tmem_ld32(taddr + (uint32_t)c, xv);
+        tmem_ld32(taddr + (uint32_t)(half_bn + c), gv);
+        tmem_ld_wait();
+        const int nout0 = (ncol0 >> 1) + c;  // output column of element 0
+        if (row_ok && nout0 < (p.N >> 1)) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
+          float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
+          if (p.bias) {
+            x0 += __ldg(p.bias + ncol0 + c + j);
+            x1 += __ldg(p.bias + ncol0 + c + j + 1);
+            g0 += __ldg(p.bias + ncol0 + half_bn + c + j);
+            g1 += __ldg(p.bias + ncol0 + half_bn + c + j + 1);
+          }
+          packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + nout0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2],
+                              packed[4 * q + 3]);
+        }
+        __syncwarp();
+      }
+    } else {
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n_first = ncol0 + c;
+        if (row_ok && n_first < p.N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n_first + j < p.N) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n_first + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+        }
+        if (p.rowvec) {
+          const float* rv = p.rowvec + (long long)batch * p.rowvec_ld + n_first;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n_first + j < p.N) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+        }
+        if (p.act == EA_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+        } else if (p.act == EA_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+        }
+        if (p.out_scale != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n_first);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n_first + q * 8 < p.N) {
+              uint4 u = __ldg(rp + q);
+              float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z),
+                     d = ea_unpack2(u.w);
+              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+              f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* dst = p.out_f32 + m * p.ldo + n_first;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n_first + j < p.N) {
+              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (p.accumulate) {
+                float4 old = *reinterpret_cast<float4*>(dst + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        } else {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + n_first);
+        if (p.accumulate) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n_first + q * 8 < p.N) {
+              uint4 u = dst[q];
+              float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z),
+                     d = ea_unpack2(u.w);
+              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+              f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+            }
+          }
+        }
+        uint4* dst2 = p.out2 ? reinterpret_cast<uint4*>(p.out2 + m * p.ldo2 + n_first) : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (n_first + q * 8 < p.N) {
+            uint4 o = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]),
+                                 ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                 ea_pack2(f[q * 8 + 4], f[q * 8 + 5]),
+                                 ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
+            dst[q] = o;
+            if (dst2) dst2[q] = o;
+          }
+        }
+        }  // half output
+        }  // row_ok
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)(p.BN < 32 ? 32 : p.BN));
+  }
+}
+
+// ------------------------------- host side ---------------------------------
+
+static int encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ea_tmap_encode()(m, EA_TMAP_DTYPE, 2, const_cast<void*>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int encode_4d(CUtensorMap* m, const void* base, const uint64_t dims_[4],
+                     const uint64_t strides_bytes[3], const uint32_t box_[4]) {
+  cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
+  cuuint64_t strides[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ea_tmap_encode()(m, EA_TMAP_DTYPE, 4, const_cast<void*>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// Tile box geometry for an output of H x W per image: bw*bh*bn == 128, powers of two.
+static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
+  bw = 1;
+  while (bw * 2 <= W && bw * 2 <= 128 && (W % (bw * 2)) == 0) bw *= 2;
+  bh = 1;
+  while (bh * 2 <= H && bw * bh * 2 <= 128 && (H % (bh * 2)) == 0) bh *= 2;
+  bn = 128 / (bw * bh);
+}
+
+static int pick_bn(int M_tiles, int N, int act) {
+  if (act == EA_ACT_GEGLU) return 128;
+  // prefer 128; fall back to 64 when it wastes less / fills more SMs
+  if (N % 128 == 0) {
+    long tiles128 = (long)M_tiles * (N / 128);
+    if (tiles128 >= 148) return 128;
+    return 64;
+  }
+  if (N % 64 == 0) return 64;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  return 128;
+}
+
+}  // namespace ea
+
+using namespace ea;
+
+extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->a || !a->w || (!a->out && !a->out_f32)) return EA_ERR_ARG;
+  if (a->mode < 0 || a->mode > 2) return EA_ERR_ARG;
+  if (a->N <= 0 || a->M <= 0) return EA_ERR_ARG;
+  if (a->N % 8 != 0) return EA_ERR_SHAPE;
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  p.mode = a->mode;
+  p.bias = a->bias;
+  p.rowvec = a->rowvec;
+  p.rows_per_batch = a->rows_per_batch;
+  p.rowvec_ld = a->rowvec_ld;
+  p.residual = reinterpret_cast<const ea_half*>(a->residual);
+  p.ldr = a->ldr;
+  p.out = reinterpret_cast<ea_half*>(a->out);
+  p.ldo = a->ldo;
+  p.out2 = reinterpret_cast<ea_half*>(a->out2);
+  p.ldo2 = a->ldo2;
+  p.out_f32 = a->out_f32;
+  p.act = a->act;
+  p.out_scale = a->out_scale;
+  p.accumulate = a->accumulate;
+  if (p.ldo % 8 != 0 || (p.residual && p.ldr % 8 != 0) || (p.out2 && p.ldo2 % 8 != 0))
+    return EA_ERR_SHAPE;
+
+  CUtensorMap tmA[4], tmAx, tmB;
+  memset(tmA, 0, sizeof(tmA));
+  memset(&tmAx, 0, sizeof(tmAx));
+  int m_tiles;
+  long long Ktot;
+  if (a->mode == EA_GEMM_LINEAR) {
+    if (a->K % 8 != 0 || a->lda % 8 != 0) return EA_ERR_SHAPE;
+    p.nkb_main = (a->K + BK - 1) / BK;
+    p.nkb_extra = 0;
+    p.cin_blocks = 1;
+    m_tiles = (a->M + BM - 1) / BM;
+    Ktot = a->K;
+    if (encode_2d(&tmA[0], a->a, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM))
+      return EA_ERR_TMAP;
+    tmA[1] = tmA[2] = tmA[3] = tmA[0];
+    tmAx = tmA[0];
+  } else {
+    const int H = a->H, W = a->W, B = a->Bsz, C = a->Cin;
+    if (C % 64 != 0 || H <= 0 || W <= 0 || B <= 0) return EA_ERR_SHAPE;
+    if ((long long)B * H * W != a->M) return EA_ERR_SHAPE;
+    p.H = H; p.W = W; p.Bsz = B;
+    conv_geometry(H, W, p.bw, p.bh, p.bn);
+    p.tiles_w = W / p.bw;
+    p.tiles_h = H / p.bh;
+    p.cin_blocks = C / 64;
+    p.nkb_main = 9 * p.cin_blocks;
+    p.nkb_extra = 0;
+    m_tiles = ((B + p.bn - 1) / p.bn) * p.tiles_w * p.tiles_h;
+    Ktot = 9LL * C;
+    const long long lda = a->lda > 0 ? a->lda : C;  // channel stride of one pixel (elements)
+    uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (a->mode == EA_GEMM_CONV_S1) {
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t st[3] = {(uint64_t)lda * 2, (uint64_t)lda * W * 2, (uint64_t)lda * W * H * 2};
+      if (encode_4d(&tmA[0], a->a, dims, st, box)) return EA_ERR_TMAP;
+      tmA[1] = tmA[2] = tmA[3] = tmA[0];
+    } else {
+      // input is (2H x 2W); four phase views (ph, pw) each of H x W
+      const int Hin = 2 * H, Win = 2 * W;
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const ea_half* base =
+              reinterpret_cast<const ea_half*>(a->a) + ((long long)ph * Win + pw) * lda;
+          uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+          uint64_t st[3] = {(uint64_t)lda * 2 * 2, (uint64_t)lda * Win * 2 * 2,
+                            (uint64_t)lda * Win * Hin * 2};
+          if (encode_4d(&tmA[ph * 2 + pw], base, dims, st, box)) return EA_ERR_TMAP;
+        }
+    }
+    tmAx = tmA[0];
+    if (a->a_extra) {
+      if (a->mode != EA_GEMM_CONV_S1 || a->Cin_extra % 64 != 0) return EA_ERR_SHAPE;
+      const long long ldx = a->ld_extra > 0 ? a->ld_extra : a->Cin_extra;
+      uint64_t dims[4] = {(uint64_t)a->Cin_extra, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t st[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * W * 2, (uint64_t)ldx * W * H * 2};
+      if (encode_4d(&tmAx, a->a_extra, dims, st, box)) return EA_ERR_TMAP;
+      p.nkb_extra = a->Cin_extra / 64;
+      Ktot += a->Cin_extra;
+    }
+  }
+  p.BN = a->force_bn > 0 ? a->force_bn : pick_bn(m_tiles, a->N, a->act);
+  if (p.BN != 32 && p.BN != 64 && p.BN != 128 && p.BN != 256) return EA_ERR_ARG;
+  if (a->act == EA_ACT_GEGLU && (a->N % p.BN != 0 || p.BN < 64)) return EA_ERR_SHAPE;
+  const long long ldw = a->ldw > 0 ? a->ldw : Ktot;
+  if (ldw % 8 != 0) return EA_ERR_SHAPE;
+  if (encode_2d(&tmB, a->w, (uint64_t)Ktot, (uint64_t)a->N, (uint64_t)ldw * 2, BK,
+                (uint32_t)p.BN))
+    return EA_ERR_TMAP;
+
+  const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  int stages = a->force_stages > 0 ? a->force_stages : (p.BN <= 128 ? 3 : 4);
+  const int nkb = p.nkb_main + p.nkb_extra;
+  if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static int max_set = 0;
+  if (smem_bytes > max_set) {
+    if (cudaFuncSetAttribute(ea_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes) != cudaSuccess)
+      return EA_ERR_CUDA;
+    max_set = smem_bytes;
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)((a->N + p.BN - 1) / p.BN), 1);
+  ea_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmAx,
+                                                             tmB, p);
+  ea_count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : EA_ERR_CUDA;
+}

@@ -1,0 +1,577 @@
+// ea_pointwise.cu — the HBM/L2-bound operators around the tensor-core kernels (sm_100a).
+// GroupNorm(+SiLU), LayerNorm, small direct convolutions, nearest upsample, the tiny
+// time-embedding linears, the fused out-conv + CFG + DDIM step, and the SAM window helpers.
+// All use 16-byte vector accesses on channels-last data and warp-shuffle reductions.
+#include "ea_common.cuh"
+#include "ea_internal.h"
+
+namespace ea {
+
+// ------------------------------- GroupNorm ---------------------------------
+// Pass 1: per-(batch, group) sum / sum-of-squares.  A CTA owns a run of pixels of one image and
+// walks them with fully coalesced row reads (thread <-> 8-channel vector); group partials are
+// combined in shared memory and flushed with one atomicAdd pair per group per CTA.
+__global__ void gn_stats_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
+                                const ea_half* __restrict__ x2, long long ldx2, int HW, int C,
+                                int groups, int pix_per_cta, float* __restrict__ ws) {
+  extern __shared__ float sh[];  // [groups*2]
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int nvec = C >> 3;
+  // thread handles vector index v (fixed) for pixels p0 + k*(blockDim/nvec_rounded)...
+  // simple mapping: flat index over (pixel, vec)
+  const int total = (p1 - p0) * nvec;
+  // accumulate per-thread for up to two groups a vector may straddle; flush via smem atomics
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    int pp = idx / nvec;
+    int v = idx - pp * nvec;
+    int c = v << 3;
+    long long pix = (long long)b * HW + p0 + pp;
+    uint4 u;
+    if (c < C1) u = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + c));
+    else u = __ldg(reinterpret_cast<const uint4*>(x2 + pix * ldx2 + (c - C1)));
+    float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
+    float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+    int g0 = c / cpg;
+    int g7 = (c + 7) / cpg;
+    if (g0 == g7) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += vals[j]; q += vals[j] * vals[j]; }
+      atomicAdd(&sh[g0 * 2], s);
+      atomicAdd(&sh[g0 * 2 + 1], q);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int g = (c + j) / cpg;
+        atomicAdd(&sh[g * 2], vals[j]);
+        atomicAdd(&sh[g * 2 + 1], vals[j] * vals[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+    atomicAdd(&ws[(long long)b * groups * 2 + i], sh[i]);
+}
+
+// Pass 2: normalise + affine (+SiLU), 8 channels per thread.
+__global__ void gn_apply_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
+                                const ea_half* __restrict__ x2, long long ldx2,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                ea_half* __restrict__ out, long long ldo, int B, int HW, int C,
+                                int groups, float eps, int silu, const float* __restrict__ ws) {
+  const int nvec = C >> 3;
+  const long long total = (long long)B * HW * nvec;
+  const int cpg = C / groups;
+  const float inv_n = 1.0f / ((float)HW * (float)cpg);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx / nvec;
+    int v = (int)(idx - pix * nvec);
+    int c = v << 3;
+    int b = (int)(pix / HW);
+    uint4 u;
+    if (c < C1) u = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + c));
+    else u = __ldg(reinterpret_cast<const uint4*>(x2 + pix * ldx2 + (c - C1)));
+    float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
+    float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    int gprev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int g = (c + j) / cpg;
+      if (g != gprev) {
+        float s = ws[((long long)b * groups + g) * 2];
+        float q = ws[((long long)b * groups + g) * 2 + 1];
+        mean = s * inv_n;
+        float var = fmaxf(q * inv_n - mean * mean, 0.f);
+        rstd = rsqrtf(var + eps);
+        gprev = g;
+      }
+      float y = (vals[j] - mean) * rstd * gm[j] + bt[j];
+      vals[j] = silu ? silu_f(y) : y;
+    }
+    uint4 o = make_uint4(ea_pack2(vals[0], vals[1]), ea_pack2(vals[2], vals[3]),
+                         ea_pack2(vals[4], vals[5]), ea_pack2(vals[6], vals[7]));
+    *reinterpret_cast<uint4*>(out + pix * ldo + c) = o;
+  }
+}
+
+// ------------------------------- LayerNorm ---------------------------------
+static constexpr int LN_MAXV = 8;  // C <= 8 * 32 * 8 = 2048
+__global__ void layernorm_kernel(const ea_half* __restrict__ x, long long ldx,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 ea_half* __restrict__ out, long long ldo, int M, int C,
+                                 float eps) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  uint4 regs[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+      regs[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + (v << 3)));
+      float2 a = ea_unpack2(regs[i].x), b = ea_unpack2(regs[i].y), c = ea_unpack2(regs[i].z),
+             d = ea_unpack2(regs[i].w);
+      s += a.x + a.y + b.x + b.y + c.x + c.y + d.x + d.y;
+    }
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+      float2 a = ea_unpack2(regs[i].x), b = ea_unpack2(regs[i].y), c = ea_unpack2(regs[i].z),
+             d = ea_unpack2(regs[i].w);
+      float t;
+      t = a.x - mean; q += t * t; t = a.y - mean; q += t * t;
+      t = b.x - mean; q += t * t; t = b.y - mean; q += t * t;
+      t = c.x - mean; q += t * t; t = c.y - mean; q += t * t;
+      t = d.x - mean; q += t * t; t = d.y - mean; q += t * t;
+    }
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    int v = lane + i * 32;
+    if (v < nvec) {
+      int c0 = v << 3;
+      float2 a = ea_unpack2(regs[i].x), b = ea_unpack2(regs[i].y), c = ea_unpack2(regs[i].z),
+             d = ea_unpack2(regs[i].w);
+      float vals[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[j] = (vals[j] - mean) * rstd * gm[j] + bt[j];
+      uint4 o = make_uint4(ea_pack2(vals[0], vals[1]), ea_pack2(vals[2], vals[3]),
+                           ea_pack2(vals[4], vals[5]), ea_pack2(vals[6], vals[7]));
+      *reinterpret_cast<uint4*>(out + row * ldo + c0) = o;
+    }
+  }
+}
+
+// ---------------------------- direct small conv ----------------------------
+// thread <-> (pixel, cout); weights [k,k,Cin,Cout] fp32 so a warp (consecutive cout) reads them
+// coalesced while the input pixel values are warp-broadcast.
+__global__ void conv_direct_kernel(const ea_half* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, ea_half* __restrict__ out,
+                                   int B, int Hin, int Win, int Cin, int Cout, int ks, int stride,
+                                   int silu, const ea_half* __restrict__ add) {
+  const int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
+  const long long total = (long long)B * Ho * Wo * Cout;
+  const int pad = ks / 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(idx % Cout);
+    long long pix = idx / Cout;
+    int wo = (int)(pix % Wo);
+    int ho = (int)((pix / Wo) % Ho);
+    int b = (int)(pix / ((long long)Wo * Ho));
+    float acc = bias ? __ldg(bias + co) : 0.f;
+    for (int kh = 0; kh < ks; ++kh) {
+      int hi = ho * stride + kh - pad;
+      if (hi < 0 || hi >= Hin) continue;
+      for (int kw = 0; kw < ks; ++kw) {
+        int wi = wo * stride + kw - pad;
+        if (wi < 0 || wi >= Win) continue;
+        const ea_half* xp = x + (((long long)b * Hin + hi) * Win + wi) * Cin;
+        const float* wp = w + ((long long)(kh * ks + kw) * Cin) * Cout + co;
+        for (int c = 0; c < Cin; ++c) acc += ea_h2f(xp[c]) * __ldg(wp + (long long)c * Cout);
+      }
+    }
+    if (silu) acc = silu_f(acc);
+    if (add) acc += ea_h2f(add[idx]);
+    out[idx] = ea_f2h(acc);
+  }
+}
+
+__global__ void upsample2x_kernel(const ea_half* __restrict__ x, ea_half* __restrict__ out, int B,
+                                  int H, int W, int C) {
+  const int nvec = C >> 3;
+  const long long total = (long long)B * (2 * H) * (2 * W) * nvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(idx % nvec);
+    long long pix = idx / nvec;
+    int wo = (int)(pix % (2 * W));
+    int ho = (int)((pix / (2 * W)) % (2 * H));
+    int b = (int)(pix / ((long long)4 * W * H));
+    const uint4* src = reinterpret_cast<const uint4*>(
+        x + (((long long)b * H + (ho >> 1)) * W + (wo >> 1)) * C + (v << 3));
+    *reinterpret_cast<uint4*>(out + pix * C + (v << 3)) = __ldg(src);
+  }
+}
+
+// y[M,N] = act_out(W[N,K] x act_in(x[M,K]) + b); one warp per output column n, M <= 16.
+__global__ void small_linear_kernel(const float* __restrict__ x, const ea_half* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y, int M,
+                                    int N, int K, int silu_in, int silu_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+  const ea_half* wr = w + (long long)n * K;
+  for (int k = lane * 8; k < K; k += 32 * 8) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+    float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), c = ea_unpack2(u.z), d = ea_unpack2(u.w);
+    float wv[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      if (m < M) {
+        const float* xr = x + (long long)m * K + k;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xv = __ldg(xr + j);
+          if (silu_in) xv = silu_f(xv);
+          acc[m] += wv[j] * xv;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    if (m < M) {
+      float s = warp_sum(acc[m]);
+      if (lane == 0) {
+        s += bias ? __ldg(bias + n) : 0.f;
+        if (silu_out) s = silu_f(s);
+        y[(long long)m * N + n] = s;
+      }
+    }
+  }
+}
+
+// util.py:154-174: freqs = exp(-ln(10000) * i / half), emb = [cos(t f) | sin(t f)]
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out,
+                                          int B, int dim) {
+  const int half = dim / 2;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * half) return;
+  int b = idx / half, i = idx - b * half;
+  float f = expf(-9.210340371976184f * (float)i / (float)half);
+  float a = t[b] * f;
+  out[(long long)b * dim + i] = cosf(a);
+  out[(long long)b * dim + half + i] = sinf(a);
+}
+
+// ---------------- out conv (C -> 4) + CFG + DDIM + inpaint blend -------------
+// One warp per (image, pixel): both CFG halves are reduced by the same warp so the guidance
+// combine and the DDIM update happen in registers.
+__global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ latents,
+                                    float* __restrict__ eps_out, const float* __restrict__ coef,
+                                    float guidance, const float* __restrict__ known,
+                                    const float* __restrict__ mask, ea_half* __restrict__ lat_half,
+                                    int Nimg, int H, int W, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long npix = (long long)Nimg * H * W;
+  if (gw >= npix) return;
+  const int img = (int)(gw / ((long long)H * W));
+  const int rem = (int)(gw - (long long)img * H * W);
+  const int h = rem / W, wq = rem - h * W;
+  float au[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < 3; ++kh) {
+    int hi = h + kh - 1;
+    if (hi < 0 || hi >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      int wi = wq + kw - 1;
+      if (wi < 0 || wi >= W) continue;
+      const ea_half* pu = xn + (((long long)img * H + hi) * W + wi) * C;
+      const ea_half* pc = xn + (((long long)(img + Nimg) * H + hi) * W + wi) * C;
+      const float* wt = w + (kh * 3 + kw) * C;  // + o*9*C
+      for (int c = lane * 8; c < C; c += 256) {
+        uint4 uu = __ldg(reinterpret_cast<const uint4*>(pu + c));
+        uint4 uc = __ldg(reinterpret_cast<const uint4*>(pc + c));
+        float2 a0 = ea_unpack2(uu.x), a1 = ea_unpack2(uu.y), a2 = ea_unpack2(uu.z),
+               a3 = ea_unpack2(uu.w);
+        float2 b0 = ea_unpack2(uc.x), b1 = ea_unpack2(uc.y), b2 = ea_unpack2(uc.z),
+               b3 = ea_unpack2(uc.w);
+        float xu[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        float xc[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float* wo = wt + (long long)o * 9 * C + c;
+          float4 w0 = __ldg(reinterpret_cast<const float4*>(wo));
+          float4 w1 = __ldg(reinterpret_cast<const float4*>(wo + 4));
+          float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            au[o] += wv[j] * xu[j];
+            ac[o] += wv[j] * xc[j];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    au[o] = warp_sum(au[o]);
+    ac[o] = warp_sum(ac[o]);
+  }
+  if (lane < 4) {
+    const int o = lane;
+    float eu = (o == 0 ? au[0] : o == 1 ? au[1] : o == 2 ? au[2] : au[3]) + bias[o];
+    float ec = (o == 0 ? ac[0] : o == 1 ? ac[1] : o == 2 ? ac[2] : ac[3]) + bias[o];
+    if (eps_out) {
+      eps_out[gw * 4 + o] = eu;
+      eps_out[(gw + npix) * 4 + o] = ec;
+    }
+    if (latents) {
+      float e = eu + guidance * (ec - eu);  // cldm/ddim_hacked.py:192
+      float sa = coef[0], s1a = coef[1], sap = coef[2], s1ap = coef[3];
+      float xt = latents[gw * 4 + o];
+      float x0 = (xt - s1a * e) / sa;       // :215
+      float xp = sap * x0 + s1ap * e;       // :226-230 (eta = 0)
+      if (known) {
+        float mk = mask[gw];
+        xp = known[gw * 4 + o] * mk + xp * (1.f - mk);
+      }
+      latents[gw * 4 + o] = xp;
+      if (lat_half) {
+        lat_half[gw * 4 + o] = ea_f2h(xp);
+        lat_half[(gw + npix) * 4 + o] = ea_f2h(xp);
+      }
+    }
+  }
+}
+
+// ------------------------------ SAM helpers --------------------------------
+__global__ void sam_relpos_kernel(const ea_half* __restrict__ q, long long q_bs, long long q_ns,
+                                  const float* __restrict__ Rh, const float* __restrict__ Rw,
+                                  float* __restrict__ rel_h, float* __restrict__ rel_w, int B,
+                                  int heads, int S, int d) {
+  const long long total = (long long)B * heads * S * S * 2 * S;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(idx % (2 * S));
+    long long t = idx / (2 * S);
+    int qi = (int)(t % (S * S));
+    long long bh = t / (S * S);
+    int hd = (int)(bh % heads);
+    int b = (int)(bh / heads);
+    int qh = qi / S, qw = qi - qh * S;
+    const ea_half* qp = q + (long long)b * q_bs + (long long)qi * q_ns + (long long)hd * d;
+    const bool is_h = kk < S;
+    int k = is_h ? kk : kk - S;
+    const float* rp = is_h ? Rh + ((long long)qh * S + k) * d : Rw + ((long long)qw * S + k) * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 2) {
+      float2 qv = ea_unpack2(*reinterpret_cast<const uint32_t*>(qp + c));
+      acc += qv.x * __ldg(rp + c) + qv.y * __ldg(rp + c + 1);
+    }
+    float* dst = is_h ? rel_h : rel_w;
+    dst[(bh * S * S + qi) * S + k] = acc;
+  }
+}
+
+__global__ void window_partition_kernel(const ea_half* __restrict__ x, ea_half* __restrict__ out,
+                                        int B, int H, int W, int C, int ws, int nWh, int nWw) {
+  const int nvec = C >> 3;
+  const long long total = (long long)B * nWh * nWw * ws * ws * nvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(idx % nvec);
+    long long t = idx / nvec;
+    int j = (int)(t % ws); t /= ws;
+    int i = (int)(t % ws); t /= ws;
+    int ww = (int)(t % nWw); t /= nWw;
+    int wh = (int)(t % nWh);
+    int b = (int)(t / nWh);
+    int h = wh * ws + i, w = ww * ws + j;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (h < H && w < W)
+      val = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + (v << 3)));
+    *reinterpret_cast<uint4*>(out + (idx / nvec) * C + (v << 3)) = val;
+  }
+}
+
+__global__ void window_unpartition_kernel(const ea_half* __restrict__ xw,
+                                          const ea_half* __restrict__ residual,
+                                          ea_half* __restrict__ out, int B, int H, int W, int C,
+                                          int ws, int nWh, int nWw) {
+  const int nvec = C >> 3;
+  const long long total = (long long)B * H * W * nvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int v = (int)(idx % nvec);
+    long long pix = idx / nvec;
+    int w = (int)(pix % W);
+    int h = (int)((pix / W) % H);
+    int b = (int)(pix / ((long long)W * H));
+    int wh = h / ws, i = h - wh * ws, ww = w / ws, j = w - ww * ws;
+    long long src = ((((long long)b * nWh + wh) * nWw + ww) * ws + i) * ws + j;
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(xw + src * C + (v << 3)));
+    if (residual) {
+      uint4 r = __ldg(reinterpret_cast<const uint4*>(residual + pix * C + (v << 3)));
+      float2 a, b2;
+      a = ea_unpack2(u.x); b2 = ea_unpack2(r.x); u.x = ea_pack2(a.x + b2.x, a.y + b2.y);
+      a = ea_unpack2(u.y); b2 = ea_unpack2(r.y); u.y = ea_pack2(a.x + b2.x, a.y + b2.y);
+      a = ea_unpack2(u.z); b2 = ea_unpack2(r.z); u.z = ea_pack2(a.x + b2.x, a.y + b2.y);
+      a = ea_unpack2(u.w); b2 = ea_unpack2(r.w); u.w = ea_pack2(a.x + b2.x, a.y + b2.y);
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + (v << 3)) = u;
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ea
+
+using namespace ea;
+#define EA_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define EA_LAUNCH_OK() (ea_count_launch(), (cudaGetLastError() == cudaSuccess ? 0 : EA_ERR_CUDA))
+
+extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
+  if (!a || !a->x || !a->out || !a->gamma || !a->beta || !a->workspace) return EA_ERR_ARG;
+  if (a->C % 8 != 0 || a->C % a->groups != 0 || a->ldx % 8 != 0 || a->ldo % 8 != 0)
+    return EA_ERR_SHAPE;
+  const int C1 = a->x2 ? a->C1 : a->C;
+  if (a->x2 && (C1 % 8 != 0 || a->ldx2 % 8 != 0)) return EA_ERR_SHAPE;
+  cudaStream_t st = EA_STREAM(stream);
+  if (cudaMemsetAsync(a->workspace, 0, sizeof(float) * 2 * a->B * a->groups, st) != cudaSuccess)
+    return EA_ERR_CUDA;
+  int chunks = a->HW >= 64 ? 64 : a->HW;
+  int ppc = (a->HW + chunks - 1) / chunks;
+  chunks = (a->HW + ppc - 1) / ppc;
+  dim3 g1(chunks, a->B);
+  gn_stats_kernel<<<g1, 256, a->groups * 2 * sizeof(float), st>>>(
+      reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
+      a->ldx2, a->HW, a->C, a->groups, ppc, a->workspace);
+  ea_count_launch();
+  long long total = (long long)a->B * a->HW * (a->C / 8);
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+      reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
+      a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->B, a->HW, a->C,
+      a->groups, a->eps, a->silu, a->workspace);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* beta,
+                            void* out, long long ldo, int M, int C, float eps, void* stream) {
+  if (!x || !out || !gamma || !beta) return EA_ERR_ARG;
+  if (C % 8 != 0 || C > 8 * 32 * LN_MAXV || ldx % 8 != 0 || ldo % 8 != 0) return EA_ERR_SHAPE;
+  const int wpc = 8;
+  layernorm_kernel<<<(M + wpc - 1) / wpc, wpc * 32, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(x), ldx, gamma, beta, reinterpret_cast<ea_half*>(out), ldo,
+      M, C, eps);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_conv_direct(const void* x, const float* w, const float* bias, void* out, int B,
+                              int Hin, int Win, int Cin, int Cout, int ksize, int stride, int silu,
+                              const void* add, void* stream) {
+  if (!x || !w || !out) return EA_ERR_ARG;
+  if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EA_ERR_SHAPE;
+  int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
+  long long total = (long long)B * Ho * Wo * Cout;
+  conv_direct_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(x), w, bias, reinterpret_cast<ea_half*>(out), B, Hin, Win,
+      Cin, Cout, ksize, stride, silu, reinterpret_cast<const ea_half*>(add));
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_upsample2x(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+  if (!x || !out) return EA_ERR_ARG;
+  if (C % 8 != 0) return EA_ERR_SHAPE;
+  long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_small_linear(const float* x, const void* w, const float* bias, float* y, int M,
+                               int N, int K, int silu_in, int silu_out, void* stream) {
+  if (!x || !w || !y) return EA_ERR_ARG;
+  if (M < 1 || M > 16 || K % 8 != 0) return EA_ERR_SHAPE;
+  const int wpc = 8;
+  small_linear_kernel<<<(N + wpc - 1) / wpc, wpc * 32, 0, EA_STREAM(stream)>>>(
+      x, reinterpret_cast<const ea_half*>(w), bias, y, M, N, K, silu_in, silu_out);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_timestep_embedding(const float* t, float* out, int B, int dim, void* stream) {
+  if (!t || !out) return EA_ERR_ARG;
+  if (dim % 2 != 0) return EA_ERR_SHAPE;
+  int total = B * dim / 2;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, EA_STREAM(stream)>>>(t, out, B, dim);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
+                               float* eps_out, const float* coef, float guidance,
+                               const float* known, const float* mask, void* lat_half_out, int Nimg,
+                               int H, int W, int C, void* stream) {
+  if (!xn || !w || !bias || (!latents && !eps_out)) return EA_ERR_ARG;
+  if (latents && !coef) return EA_ERR_ARG;
+  if (known && !mask) return EA_ERR_ARG;
+  if (C % 8 != 0) return EA_ERR_SHAPE;
+  long long npix = (long long)Nimg * H * W;
+  const int wpc = 4;
+  out_cfg_ddim_kernel<<<(unsigned)((npix + wpc - 1) / wpc), wpc * 32, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, mask,
+      reinterpret_cast<ea_half*>(lat_half_out), Nimg, H, W, C);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_sam_relpos(const void* q, long long q_bs, long long q_ns, const float* Rh,
+                             const float* Rw, float* rel_h, float* rel_w, int B, int heads, int S,
+                             int d, void* stream) {
+  if (!q || !Rh || !Rw || !rel_h || !rel_w) return EA_ERR_ARG;
+  if (d % 2 != 0) return EA_ERR_SHAPE;
+  long long total = (long long)B * heads * S * S * 2 * S;
+  sam_relpos_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(q), q_bs, q_ns, Rh, Rw, rel_h, rel_w, B, heads, S, d);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_window_partition(const void* x, void* out, int B, int H, int W, int C, int ws,
+                                   void* stream) {
+  if (!x || !out) return EA_ERR_ARG;
+  if (C % 8 != 0 || ws <= 0) return EA_ERR_SHAPE;
+  int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
+  long long total = (long long)B * nWh * nWw * ws * ws * (C / 8);
+  window_partition_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh,
+      nWw);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_window_unpartition(const void* xw, const void* residual, void* out, int B, int H,
+                                     int W, int C, int ws, void* stream) {
+  if (!xw || !out) return EA_ERR_ARG;
+  if (C % 8 != 0 || ws <= 0) return EA_ERR_SHAPE;
+  int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
+  long long total = (long long)B * H * W * (C / 8);
+  window_unpartition_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(xw), reinterpret_cast<const ea_half*>(residual),
+      reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh, nWw);
+  return EA_LAUNCH_OK();
+}

@@ -1,0 +1,188 @@
+"""Thin torch-tensor wrappers over the C ABI (include/editanything_b200.h).
+
+PyTorch is used here only for device memory and streams; every function below launches
+hand-written sm_100a kernels from libea_b200.so on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_DT = {"float16": torch.float16, "bfloat16": torch.bfloat16}
+
+
+def half_dtype():
+    return _DT[L.load().ea_dtype_name().decode()]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return L.load().ea_launch_count()
+
+
+def reset_launch_count():
+    L.load().ea_reset_launch_count()
+
+
+def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
+         conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
+         out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
+         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0):
+    """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes."""
+    lib = L.lib()
+    g = L.GemmArgs()
+    g.mode = mode
+    g.N = N if N is not None else w.shape[0]
+    if mode == L.EA_GEMM_LINEAR:
+        g.M = M if M is not None else a.shape[0]
+        g.K = K if K is not None else a.shape[-1]
+        g.lda = lda if lda is not None else a.stride(0)
+    else:
+        B, H, W_, Cin = conv
+        g.M = B * H * W_
+        g.K = 0
+        g.Bsz, g.H, g.W, g.Cin = B, H, W_, Cin
+        g.lda = lda if lda is not None else 0
+    g.a = a.data_ptr()
+    g.w = w.data_ptr()
+    g.ldw = ldw
+    if a_extra is not None:
+        g.a_extra = a_extra.data_ptr()
+        g.Cin_extra = a_extra.shape[-1]
+        g.ld_extra = ld_extra
+    g.bias = bias.data_ptr() if bias is not None else None
+    if rowvec is not None:
+        g.rowvec = rowvec.data_ptr()
+        g.rowvec_ld = rowvec.stride(0)
+    g.rows_per_batch = rows_per_batch
+    n_out = g.N // 2 if act == L.EA_ACT_GEGLU else g.N
+    if out is None and out_f32 is None:
+        out = torch.empty((g.M, n_out), device=a.device, dtype=half_dtype())
+    if residual is not None:
+        g.residual = residual.data_ptr()
+        g.ldr = ldr if ldr is not None else residual.stride(-2)
+    if out is not None:
+        g.out = out.data_ptr()
+        g.ldo = ldo if ldo is not None else out.stride(-2)
+    if out2 is not None:
+        g.out2 = out2.data_ptr()
+        g.ldo2 = ldo2 if ldo2 is not None else out2.stride(-2)
+    if out_f32 is not None:
+        g.out_f32 = out_f32.data_ptr()
+        g.ldo = ldo if ldo is not None else out_f32.stride(-2)
+    g.act = act
+    g.out_scale = out_scale
+    g.accumulate = 1 if accumulate else 0
+    g.force_bn = force_bn
+    g.force_stages = force_stages
+    L.check(lib.ea_gemm(C.byref(g), _stream()), "ea_gemm")
+    return out if out is not None else out_f32
+
+
+def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_strides, o_strides,
+              scale, rel_h=None, rel_w=None, rel_s=0):
+    """q/k/v are base tensors; *_strides = (batch_stride, row_stride) in elements."""
+    lib = L.lib()
+    a = L.AttnArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.B, a.heads, a.Nq, a.Nkv, a.d = B, heads, Nq, Nkv, d
+    a.q_bs, a.q_ns = q_strides
+    a.k_bs, a.k_ns = k_strides
+    a.v_bs, a.v_ns = v_strides
+    a.o_bs, a.o_ns = o_strides
+    a.scale = scale
+    if rel_h is not None:
+        a.rel_h, a.rel_w, a.rel_s = rel_h.data_ptr(), rel_w.data_ptr(), rel_s
+    L.check(lib.ea_attention(C.byref(a), _stream()), "ea_attention")
+    return out
+
+
+def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True, workspace=None,
+              x2=None, C1=0, ldx=None, ldx2=None, ldo=None):
+    lib = L.lib()
+    g = L.GnArgs()
+    g.x = x.data_ptr()
+    g.ldx = ldx if ldx is not None else (C1 if x2 is not None else C_)
+    if x2 is not None:
+        g.x2 = x2.data_ptr()
+        g.C1 = C1
+        g.ldx2 = ldx2 if ldx2 is not None else (C_ - C1)
+    g.gamma, g.beta = gamma.data_ptr(), beta.data_ptr()
+    g.out = out.data_ptr()
+    g.ldo = ldo if ldo is not None else C_
+    g.B, g.HW, g.C, g.groups = B, HW, C_, groups
+    g.eps, g.silu = eps, 1 if silu else 0
+    if workspace is None:
+        workspace = torch.empty(B * groups * 2, device=x.device, dtype=torch.float32)
+    g.workspace = workspace.data_ptr()
+    L.check(lib.ea_groupnorm(C.byref(g), _stream()), "ea_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, out, *, M, C_, eps=1e-5, ldx=None, ldo=None):
+    lib = L.lib()
+    L.check(lib.ea_layernorm(_p(x), ldx if ldx is not None else C_, _p(gamma), _p(beta), _p(out),
+                             ldo if ldo is not None else C_, M, C_, eps, _stream()), "ea_layernorm")
+    return out
+
+
+def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, silu=False, add=None):
+    """w: fp32 [k, k, Cin, Cout]."""
+    lib = L.lib()
+    L.check(lib.ea_conv_direct(_p(x), _p(w), _p(bias), _p(out), B, Hin, Win, Cin, Cout, ksize, stride,
+                               1 if silu else 0, _p(add), _stream()), "ea_conv_direct")
+    return out
+
+
+def upsample2x(x, out, *, B, H, W, C_):
+    lib = L.lib()
+    L.check(lib.ea_upsample2x(_p(x), _p(out), B, H, W, C_, _stream()), "ea_upsample2x")
+    return out
+
+
+def small_linear(x, w, bias, y, *, M, N, K, silu_in=False, silu_out=False):
+    lib = L.lib()
+    L.check(lib.ea_small_linear(_p(x), _p(w), _p(bias), _p(y), M, N, K, 1 if silu_in else 0,
+                                1 if silu_out else 0, _stream()), "ea_small_linear")
+    return y
+
+
+def timestep_embedding(t, out, *, B, dim):
+    lib = L.lib()
+    L.check(lib.ea_timestep_embedding(_p(t), _p(out), B, dim, _stream()), "ea_timestep_embedding")
+    return out
+
+
+def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None,
+                 mask=None, lat_half_out=None, Nimg, H, W, C_):
+    lib = L.lib()
+    L.check(lib.ea_out_cfg_ddim(_p(xn), _p(w), _p(bias), _p(latents), _p(eps_out), _p(coef),
+                                float(guidance), _p(known), _p(mask), _p(lat_half_out), Nimg, H, W,
+                                C_, _stream()), "ea_out_cfg_ddim")
+
+
+def sam_relpos(q, q_bs, q_ns, Rh, Rw, rel_h, rel_w, *, B, heads, S, d):
+    lib = L.lib()
+    L.check(lib.ea_sam_relpos(_p(q), q_bs, q_ns, _p(Rh), _p(Rw), _p(rel_h), _p(rel_w), B, heads, S, d,
+                              _stream()), "ea_sam_relpos")
+
+
+def window_partition(x, out, *, B, H, W, C_, ws):
+    lib = L.lib()
+    L.check(lib.ea_window_partition(_p(x), _p(out), B, H, W, C_, ws, _stream()), "ea_window_partition")
+    return out
+
+
+def window_unpartition(xw, residual, out, *, B, H, W, C_, ws):
+    lib = L.lib()
+    L.check(lib.ea_window_unpartition(_p(xw), _p(residual), _p(out), B, H, W, C_, ws, _stream()),
+            "ea_window_unpartition")
+    return out

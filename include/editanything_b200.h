@@ -1,0 +1,194 @@
+/* editanything_b200.h — C ABI of libea_b200.so (B200 / sm_100a only).
+ *
+ * The reference (sail-sg/EditAnything @ 8d2db4ae) is pure Python and has no FFI, plugin or
+ * operator-registration interface: its hot path bottoms out in torch.nn
+ * modules.  This header is therefore the boundary a maintainer would bind INSTEAD of those
+ * torch.nn calls: one entry point per fused operator of the per-step network
+ * (ControlNet(s) -> UNet -> CFG -> DDIM) and of the SAM ViT-H image encoder.  Each entry point
+ * cites the reference function whose arithmetic it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding and where each call slots into the reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - all tensor pointers are DEVICE pointers owned by the caller
+ *   - activations are channels-last: images are NHWC [B, H, W, C], token matrices are [M, C]
+ *   - "half" means the library storage type reported by ea_dtype_name(): "float16" (default
+ *     build) or "bfloat16" (-DEA_USE_BF16); accumulation is always fp32
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates, never throws; returns 0 or a negative ea_status
+ *   - not re-entrant per stream; one process per GPU
+ */
+#ifndef EDITANYTHING_B200_H
+#define EDITANYTHING_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum ea_status {
+  EA_OK = 0,
+  EA_ERR_ARG = -1,    /* null pointer / bad enum */
+  EA_ERR_SHAPE = -2,  /* unsupported shape or alignment */
+  EA_ERR_TMAP = -3,   /* cuTensorMapEncodeTiled failed */
+  EA_ERR_CUDA = -4,   /* launch / runtime error */
+  EA_ERR_NODRIVER = -5
+};
+
+enum ea_gemm_mode { EA_GEMM_LINEAR = 0, EA_GEMM_CONV_S1 = 1, EA_GEMM_CONV_S2 = 2 };
+enum ea_act { EA_ACT_NONE = 0, EA_ACT_SILU = 1, EA_ACT_GELU = 2, EA_ACT_GEGLU = 3 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+int ea_version(void);
+const char* ea_dtype_name(void);      /* "float16" | "bfloat16" */
+const char* ea_strerror(int status);
+int ea_init(void);                    /* resolves cuTensorMapEncodeTiled; 0 on success */
+long long ea_launch_count(void);      /* kernels launched by this library since reset */
+void ea_reset_launch_count(void);
+
+/* ---- ea_gemm: tcgen05 GEMM / implicit-GEMM convolution ------------------------------------
+ * out[M,N] = epilogue( A[M,K] * W[N,K]^T )
+ * Replaces: nn.Linear / 1x1 nn.Conv2d / 3x3 nn.Conv2d (stride 1 and 2, pad 1) of
+ *   ResBlock._forward            ldm/modules/diffusionmodules/openaimodel.py:254-274
+ *   Downsample.forward           ldm/modules/diffusionmodules/openaimodel.py:133-159
+ *   Upsample.forward (conv part) ldm/modules/diffusionmodules/openaimodel.py:90-118
+ *   CrossAttention to_q/k/v/out  ldm/modules/attention.py:154-161,166-194
+ *   GEGLU / FeedForward          ldm/modules/attention.py:49-76
+ *   SpatialTransformer proj_in/out  ldm/modules/attention.py:296-318
+ *   ControlNet zero convs        cldm/cldm.py:281-282,293-303
+ *   SAM ViT-H qkv / proj / MLP / neck (segment_anything image_encoder)
+ * mode LINEAR : A is [M, lda] half.
+ * mode CONV_S1: A is NHWC [Bsz, H, W, Cin] (pixel stride lda elements, default Cin), M = Bsz*H*W,
+ *               W is [N, 9*Cin (+Cin_extra)] with K index = (kh*3+kw)*Cin + c.
+ *               a_extra (optional): NHWC [Bsz,H,W,Cin_extra] raw block input whose 1x1
+ *               skip-connection conv is folded in as extra K columns (openaimodel.py:233-240).
+ * mode CONV_S2: A is NHWC [Bsz, 2H, 2W, Cin]; H, W are the OUTPUT size.
+ * Epilogue order: +bias[n] -> +rowvec[batch(m), n] -> act -> *out_scale -> +residual[m,n]
+ *                 -> (+= out[m,n] if accumulate) -> store out (and out2).
+ * act GEGLU: W rows must be pre-interleaved per 128-row block as [64 value rows | 64 gate rows];
+ *            output has N/2 columns: value * gelu(gate)   (attention.py:54-56).
+ * Constraints: N % 8 == 0, K % 8 == 0, Cin % 64 == 0, all leading dims % 8 == 0,
+ *              pointers 16-byte aligned.
+ */
+typedef struct ea_gemm_args {
+  int mode;
+  int M, N, K;               /* K used by LINEAR only */
+  const void* a;             /* half */
+  long long lda;             /* LINEAR: row stride; CONV: pixel stride (0 -> Cin) */
+  const void* w;             /* half [N, ldw] */
+  long long ldw;             /* 0 -> total K */
+  int Bsz, H, W, Cin;        /* CONV: output spatial size, input channels */
+  const void* a_extra;       /* CONV_S1 only, optional */
+  int Cin_extra;
+  long long ld_extra;
+  const float* bias;         /* [N] fp32 or NULL */
+  const float* rowvec;       /* [batches, rowvec_ld] fp32 or NULL (time-embedding add) */
+  int rowvec_ld;
+  int rows_per_batch;        /* LINEAR: rows per batch element for rowvec (0 -> batch 0) */
+  const void* residual;      /* half [M, ldr] or NULL */
+  long long ldr;
+  void* out;                 /* half [M, ldo] */
+  long long ldo;
+  void* out2;                /* optional second destination (skip-concat slot) */
+  long long ldo2;
+  float* out_f32;            /* if non-NULL, write fp32 [M, ldo] here instead of out */
+  int act;
+  float out_scale;           /* set 1.0f when unused */
+  int accumulate;
+  int force_bn;              /* 0 = auto; else 32/64/128/256 (testing) */
+  int force_stages;          /* 0 = auto */
+} ea_gemm_args;
+int ea_gemm(const ea_gemm_args* args, void* stream);
+
+/* ---- ea_attention: fused softmax(Q K^T * scale [+ rel-pos bias]) V -------------------------
+ * Replaces CrossAttention.forward core  ldm/modules/attention.py:170-193 (QK^T in fp32,
+ * softmax, PV) and SAM Attention.forward (decomposed rel-pos).
+ * q: [B, Nq, heads, d] with strides (q_bs, q_ns, d) elements; k, v likewise with Nkv rows;
+ * out: [B, Nq, heads*d] contiguous rows of stride o_ns.  d % 8 == 0, d <= 160.
+ * rel_h / rel_w (optional, fp32 [B*heads, Nq, rel_s]): bias[q, kk] = rel_h[q, kk / rel_s] +
+ * rel_w[q, kk % rel_s] added to the scaled logits (SAM add_decomposed_rel_pos).
+ */
+typedef struct ea_attn_args {
+  const void* q; const void* k; const void* v; void* out;
+  int B, heads, Nq, Nkv, d;
+  long long q_bs, q_ns, k_bs, k_ns, v_bs, v_ns, o_bs, o_ns;  /* batch / row strides (elements) */
+  float scale;
+  const float* rel_h; const float* rel_w; int rel_s;
+} ea_attn_args;
+int ea_attention(const ea_attn_args* args, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------
+ * ea_groupnorm: GroupNorm32 (fp32 statistics) + optional SiLU on NHWC half.
+ *   Replaces normalization()+SiLU  openaimodel.py:196-200,216-219 ; util.py:217-219 ;
+ *   Normalize (eps 1e-6)  attention.py:88-89.
+ *   x may be a channel-concatenation of two tensors x[.., 0:C1] ++ x2[.., 0:C-C1]
+ *   (skip-concat, cldm/cldm.py:39-41); pass x2 = NULL for a single source.
+ * ea_layernorm: nn.LayerNorm over the last dim of [M, C]  (attention.py:263-265).
+ */
+typedef struct ea_gn_args {
+  const void* x; long long ldx; int C1;
+  const void* x2; long long ldx2;
+  const float* gamma; const float* beta;
+  void* out; long long ldo;
+  int B, HW, C, groups;
+  float eps; int silu;
+  float* workspace;          /* >= B*groups*2 floats */
+} ea_gn_args;
+int ea_groupnorm(const ea_gn_args* args, void* stream);
+int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, void* out,
+                 long long ldo, int M, int C, float eps, void* stream);
+/* LayerNorm2d over channels of NHWC == ea_layernorm on [B*H*W, C]. */
+
+/* ---- small / memory-bound operators -------------------------------------------------------
+ * ea_conv_direct: generic small 3x3 / 1x1 conv on CUDA cores (NHWC half, fp32 weights
+ *   [Cout, kh, kw, Cin]), pad = ksize/2, stride 1 or 2, optional SiLU.  Used for the ControlNet
+ *   hint stack (cldm/cldm.py:147-163), conv_in 4->320 (openaimodel.py:533-539) and the SAM
+ *   patch embedding when expressed as a GEMM prologue.
+ * ea_upsample2x: nearest x2 on NHWC (openaimodel.py:110-116).
+ * ea_small_linear: y[M<=16, N] = act_out( W[N,K] * act_in(x[M,K]) + b ), fp32 in/out, half
+ *   weights; time_embed and ResBlock.emb_layers (openaimodel.py:526-531,204-210).
+ * ea_timestep_embedding: util.py:154-174 (cos | sin, max_period 10000).
+ */
+int ea_conv_direct(const void* x, const float* w, const float* bias, void* out, int B, int Hin,
+                   int Win, int Cin, int Cout, int ksize, int stride, int silu,
+                   const void* add, void* stream);
+int ea_upsample2x(const void* x, void* out, int B, int H, int W, int C, void* stream);
+int ea_small_linear(const float* x, const void* w, const float* bias, float* y, int M, int N,
+                    int K, int silu_in, int silu_out, void* stream);
+int ea_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+
+/* ---- ea_out_cfg_ddim: final conv + classifier-free guidance + DDIM update ------------------
+ * Replaces UNetModel.out conv (openaimodel.py:726-730) on the already GroupNorm+SiLU'd input,
+ * the CFG combine (cldm/ddim_hacked.py:192; utils/stable_diffusion_controlnet_inpaint.py:1627-1631),
+ * the DDIM eta=0 update (cldm/ddim_hacked.py:203-231) and the inpaint latent blend
+ * (utils/stable_diffusion_controlnet_inpaint.py:1647-1656) in one launch.
+ * xn: NHWC half [2*Nimg, H, W, C] (first Nimg = unconditional, last Nimg = conditional);
+ * w: fp32 [4, 3, 3, C]; bias fp32 [4]; latents fp32 NHWC [Nimg, H, W, 4] updated in place;
+ * eps_out (optional) fp32 [2*Nimg, H, W, 4] raw network output;
+ * coef: device fp32 [4] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)};
+ * blend (optional): known fp32 NHWC [Nimg,H,W,4], mask fp32 [Nimg,H,W] (1 = keep known).
+ * lat_half_out (optional): half NHWC [2*Nimg,H,W,4] = updated latents duplicated for next step.
+ */
+int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
+                    float* eps_out, const float* coef, float guidance, const float* known,
+                    const float* mask, void* lat_half_out, int Nimg, int H, int W, int C,
+                    void* stream);
+
+/* ---- SAM helpers ---------------------------------------------------------------------------
+ * ea_sam_relpos: rel_h[bh, q, kh] = sum_c q[bh, q, c] * Rh[qh(q), kh, c] (and rel_w), the
+ *   decomposed relative position terms of SAM attention (HF modeling_sam.py
+ *   :789-801).  q: [B, S*S, heads, d] (strides q_bs, q_ns); Rh, Rw: fp32 [S, S, d] (already
+ *   gathered by get_rel_pos); outputs fp32 [B*heads, S*S, S].
+ * ea_window_partition / ea_window_unpartition: [B,H,W,C] <-> [B*nW, ws, ws, C] with zero pad
+ *   (modeling_sam.py:900-952).
+ */
+int ea_sam_relpos(const void* q, long long q_bs, long long q_ns, const float* Rh, const float* Rw,
+                  float* rel_h, float* rel_w, int B, int heads, int S, int d, void* stream);
+int ea_window_partition(const void* x, void* out, int B, int H, int W, int C, int ws,
+                        void* stream);
+int ea_window_unpartition(const void* xw, const void* residual, void* out, int B, int H, int W,
+                          int C, int ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDITANYTHING_B200_H */
