@@ -68,7 +68,7 @@ SYMBOLS = {
     "ea_attention": (_I, [C.POINTER(AttnArgs), _P]),
     "ea_groupnorm": (_I, [C.POINTER(GnArgs), _P]),
     "ea_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
-    "ea_conv_direct": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ea_conv_direct": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "ea_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ea_small_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),

@@ -177,7 +177,7 @@ __global__ void layernorm_kernel(const ea_half* __restrict__ x, long long ldx,
 __global__ void conv_direct_kernel(const ea_half* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ bias, ea_half* __restrict__ out,
                                    int B, int Hin, int Win, int Cin, int Cout, int ks, int stride,
-                                   int silu, const ea_half* __restrict__ add) {
+                                   int silu, const ea_half* __restrict__ add, long long ldo) {
   const int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
   const long long total = (long long)B * Ho * Wo * Cout;
   const int pad = ks / 2;
@@ -202,7 +202,7 @@ __global__ void conv_direct_kernel(const ea_half* __restrict__ x, const float* _
     }
     if (silu) acc = silu_f(acc);
     if (add) acc += ea_h2f(add[idx]);
-    out[idx] = ea_f2h(acc);
+    out[pix * ldo + co] = ea_f2h(acc);
   }
 }
 
@@ -487,14 +487,14 @@ extern "C" int ea_layernorm(const void* x, long long ldx, const float* gamma, co
 
 extern "C" int ea_conv_direct(const void* x, const float* w, const float* bias, void* out, int B,
                               int Hin, int Win, int Cin, int Cout, int ksize, int stride, int silu,
-                              const void* add, void* stream) {
+                              const void* add, long long ldo, void* stream) {
   if (!x || !w || !out) return EA_ERR_ARG;
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EA_ERR_SHAPE;
   int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
   long long total = (long long)B * Ho * Wo * Cout;
   conv_direct_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
       reinterpret_cast<const ea_half*>(x), w, bias, reinterpret_cast<ea_half*>(out), B, Hin, Win,
-      Cin, Cout, ksize, stride, silu, reinterpret_cast<const ea_half*>(add));
+      Cin, Cout, ksize, stride, silu, reinterpret_cast<const ea_half*>(add), ldo > 0 ? ldo : Cout);
   return EA_LAUNCH_OK();
 }
 

@@ -1,0 +1,385 @@
+"""Host-side executor of the SD UNet / ControlNet on the libea_b200 C-ABI operators.
+
+Mirrors the reference call contracts:
+    controlnet(sample, t, encoder_hidden_states, controlnet_cond, conditioning_scale) -> residuals
+    unet(sample, t, encoder_hidden_states, down_block_additional_residuals, mid_...)  -> eps
+but executes them channels-last on hand-written sm_100a kernels, with the ControlNet residuals
+never materialised as separate tensors: every zero-conv GEMM accumulates `scale * residual`
+straight into the UNet's skip-concat buffers (cldm/cldm.py:34-41), and CFG + the DDIM update run in
+the epilogue of the final convolution (cldm/ddim_hacked.py:190-231).
+
+Reference semantics followed (paths relative to the reference root):
+    ControlledUnetModel.forward   cldm/cldm.py:22-45
+    ControlNet.forward            cldm/cldm.py:284-305
+    ResBlock._forward             ldm/modules/diffusionmodules/openaimodel.py:254-274
+    SpatialTransformer.forward    ldm/modules/attention.py:321-340
+    BasicTransformerBlock         ldm/modules/attention.py:271-275
+"""
+import torch
+
+from . import _lib as L
+from . import ops as _cuda_ops
+from .unet_spec import HINT_STRIDES, UNetConfig, build_topology
+
+
+def _conv3_pack(w):  # [Cout, Cin, 3, 3] -> [Cout, (kh, kw, Cin)]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _geglu_interleave(n_inner):
+    """Row permutation so each 128-row block of the GEGLU projection holds 64 value rows followed
+    by their 64 gate rows (attention.py:54-56 chunks [value | gate] along the last dim)."""
+    idx = []
+    for j in range(n_inner // 64):
+        idx.append(torch.arange(j * 64, j * 64 + 64))
+        idx.append(n_inner + torch.arange(j * 64, j * 64 + 64))
+    return torch.cat(idx)
+
+
+class PackedNet:
+    """Device-resident, kernel-layout weights of one UNet or ControlNet (built once, after any LoRA
+    merge — editany_lora.py:197-329 merges LoRA deltas into the weights in place)."""
+
+    def __init__(self, cfg: UNetConfig, kind: str, state_dict, device, backend=None):
+        self.cfg, self.kind = cfg, kind
+        self.ops = backend or _cuda_ops
+        self.dev = device
+        self.hdt = self.ops.half_dtype()
+        self.topo = build_topology(cfg, with_decoder=(kind == "unet"))
+        sd = state_dict
+        self.w = {}
+        H, F = self._half, self._f32
+
+        # time embedding MLP + every ResBlock's emb projection as ONE matrix
+        self.w["te0.w"], self.w["te0.b"] = H(sd["time_embed.0.weight"]), F(sd["time_embed.0.bias"])
+        self.w["te2.w"], self.w["te2.b"] = H(sd["time_embed.2.weight"]), F(sd["time_embed.2.bias"])
+        emb_w, emb_b, self.emb_off = [], [], {}
+        off = 0
+        blocks = [b for layers in self.topo.input_blocks for b in layers] + list(self.topo.middle)
+        if kind == "unet":
+            blocks += [b for layers in self.topo.output_blocks for b in layers]
+        for b in blocks:
+            if b.kind == "res":
+                p = b.prefix
+                emb_w.append(sd[p + ".emb_layers.1.weight"])
+                # conv1 bias folded into the per-(batch, channel) row vector
+                emb_b.append(sd[p + ".emb_layers.1.bias"] + sd[p + ".in_layers.2.bias"])
+                self.emb_off[p] = off
+                off += b.cout
+        self.emb_total = off
+        self.w["emb.w"], self.w["emb.b"] = H(torch.cat(emb_w, 0)), F(torch.cat(emb_b, 0))
+
+        for b in blocks:
+            p = b.prefix
+            if b.kind == "conv_in":
+                self.w[p + ".w"] = F(sd[p + ".weight"].permute(2, 3, 1, 0))  # [k,k,Cin,Cout]
+                self.w[p + ".b"] = F(sd[p + ".bias"])
+            elif b.kind == "res":
+                for n in ("in_layers.0", "out_layers.0"):
+                    self.w[f"{p}.{n}.g"], self.w[f"{p}.{n}.b"] = F(sd[f"{p}.{n}.weight"]), F(sd[f"{p}.{n}.bias"])
+                self.w[p + ".conv1.w"] = H(_conv3_pack(sd[p + ".in_layers.2.weight"]))
+                w2 = _conv3_pack(sd[p + ".out_layers.3.weight"])
+                b2 = sd[p + ".out_layers.3.bias"]
+                if b.cin != b.cout:  # fold the 1x1 skip conv in as extra K columns
+                    w2 = torch.cat([w2, sd[p + ".skip_connection.weight"].reshape(b.cout, b.cin)], 1)
+                    b2 = b2 + sd[p + ".skip_connection.bias"]
+                self.w[p + ".conv2.w"], self.w[p + ".conv2.b"] = H(w2), F(b2)
+            elif b.kind == "attn":
+                self._pack_attn(sd, p, b.cin)
+            elif b.kind == "down":
+                self.w[p + ".w"], self.w[p + ".b"] = H(_conv3_pack(sd[p + ".op.weight"])), F(sd[p + ".op.bias"])
+            elif b.kind == "up":
+                self.w[p + ".w"], self.w[p + ".b"] = H(_conv3_pack(sd[p + ".conv.weight"])), F(sd[p + ".conv.bias"])
+        if kind == "unet":
+            self.w["out.g"], self.w["out.b"] = F(sd["out.0.weight"]), F(sd["out.0.bias"])
+            self.w["out.w"] = F(sd["out.2.weight"].permute(0, 2, 3, 1))  # [4,3,3,C]
+            self.w["out.cb"] = F(sd["out.2.bias"])
+        else:
+            for i in range(len(HINT_STRIDES)):
+                p = f"input_hint_block.{2 * i}"
+                self.w[p + ".w"] = F(sd[p + ".weight"].permute(2, 3, 1, 0))
+                self.w[p + ".b"] = F(sd[p + ".bias"])
+            for i, c in enumerate(self.topo.input_chans):
+                p = f"zero_convs.{i}.0"
+                self.w[p + ".w"], self.w[p + ".b"] = H(sd[p + ".weight"].reshape(c, c)), F(sd[p + ".bias"])
+            c = self.topo.middle[-1].cout
+            self.w["mid_out.w"] = H(sd["middle_block_out.0.weight"].reshape(c, c))
+            self.w["mid_out.b"] = F(sd["middle_block_out.0.bias"])
+
+    def _half(self, t):
+        return t.detach().to(device=self.dev, dtype=self.hdt).contiguous()
+
+    def _f32(self, t):
+        return t.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+
+    def _pack_attn(self, sd, p, c):
+        H, F = self._half, self._f32
+        heads, dh = self.cfg.heads_for(c)
+        inner = heads * dh
+        tb = p + ".transformer_blocks.0"
+        self.w[p + ".norm.g"], self.w[p + ".norm.b"] = F(sd[p + ".norm.weight"]), F(sd[p + ".norm.bias"])
+        self.w[p + ".proj_in.w"] = H(sd[p + ".proj_in.weight"].reshape(inner, c))
+        self.w[p + ".proj_in.b"] = F(sd[p + ".proj_in.bias"])
+        self.w[p + ".proj_out.w"] = H(sd[p + ".proj_out.weight"].reshape(c, inner))
+        self.w[p + ".proj_out.b"] = F(sd[p + ".proj_out.bias"])
+        self.w[p + ".qkv1.w"] = H(torch.cat([sd[f"{tb}.attn1.to_q.weight"], sd[f"{tb}.attn1.to_k.weight"],
+                                             sd[f"{tb}.attn1.to_v.weight"]], 0))
+        self.w[p + ".o1.w"], self.w[p + ".o1.b"] = H(sd[f"{tb}.attn1.to_out.0.weight"]), F(sd[f"{tb}.attn1.to_out.0.bias"])
+        self.w[p + ".q2.w"] = H(sd[f"{tb}.attn2.to_q.weight"])
+        self.w[p + ".kv2.w"] = H(torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], 0))
+        self.w[p + ".o2.w"], self.w[p + ".o2.b"] = H(sd[f"{tb}.attn2.to_out.0.weight"]), F(sd[f"{tb}.attn2.to_out.0.bias"])
+        idx = _geglu_interleave(inner * 4)
+        self.w[p + ".ff1.w"] = H(sd[f"{tb}.ff.net.0.proj.weight"][idx])
+        self.w[p + ".ff1.b"] = F(sd[f"{tb}.ff.net.0.proj.bias"][idx])
+        self.w[p + ".ff2.w"], self.w[p + ".ff2.b"] = H(sd[f"{tb}.ff.net.2.weight"]), F(sd[f"{tb}.ff.net.2.bias"])
+        for n in ("norm1", "norm2", "norm3"):
+            self.w[f"{p}.{n}.g"], self.w[f"{p}.{n}.b"] = F(sd[f"{tb}.{n}.weight"]), F(sd[f"{tb}.{n}.bias"])
+
+    def weight_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+    # ------------------------------------------------------------------ per-prompt / per-image
+    def attn_prefixes(self):
+        out = []
+        groups = list(self.topo.input_blocks) + [self.topo.middle] + list(self.topo.output_blocks)
+        for layers in groups:
+            out += [b.prefix for b in layers if b.kind == "attn"]
+        return out
+
+    def precompute_context(self, ctx):
+        """Cross-attention K/V depend only on the prompt: project them once per request
+        (attention.py:168-169 recomputes them every step)."""
+        B, Lc, D = ctx.shape
+        ctx2 = ctx.to(self.hdt).reshape(B * Lc, D).contiguous()
+        kv = {}
+        for p in self.attn_prefixes():
+            kv[p] = self.ops.gemm(ctx2, self.w[p + ".kv2.w"])  # [B*L, 2*inner]
+        return {"kv": kv, "B": B, "L": Lc}
+
+    def precompute_hint(self, hint_nchw):
+        """ControlNet.input_hint_block (cldm/cldm.py:147-163): independent of x and t, so hoisted
+        out of the denoising loop (the reference recomputes it every step, cldm/cldm.py:288)."""
+        o = self.ops
+        B, C, Hh, Wh = hint_nchw.shape
+        x = hint_nchw.permute(0, 2, 3, 1).contiguous().to(self.hdt)
+        cin = C
+        for i, s in enumerate(HINT_STRIDES):
+            p = f"input_hint_block.{2 * i}"
+            cout = self.w[p + ".w"].shape[-1]
+            Ho, Wo = (Hh + s - 1) // s, (Wh + s - 1) // s
+            y = torch.empty(B, Ho, Wo, cout, device=self.dev, dtype=self.hdt)
+            o.conv_direct(x, self.w[p + ".w"], self.w[p + ".b"], y, B=B, Hin=Hh, Win=Wh, Cin=cin, Cout=cout,
+                          ksize=3, stride=s, silu=(i != len(HINT_STRIDES) - 1))
+            x, cin, Hh, Wh = y, cout, Ho, Wo
+        return x
+
+    # ------------------------------------------------------------------ execution
+    def _emb(self, t_dev, B):
+        o = self.ops
+        mc = self.cfg.model_channels
+        te = torch.empty(B, mc, device=self.dev, dtype=torch.float32)
+        o.timestep_embedding(t_dev, te, B=B, dim=mc)
+        e1 = torch.empty(B, 4 * mc, device=self.dev, dtype=torch.float32)
+        o.small_linear(te, self.w["te0.w"], self.w["te0.b"], e1, M=B, N=4 * mc, K=mc, silu_out=True)
+        # emb = te2(e1); every consumer applies SiLU first (openaimodel.py:204-205) -> silu_out here
+        e2 = torch.empty(B, 4 * mc, device=self.dev, dtype=torch.float32)
+        o.small_linear(e1, self.w["te2.w"], self.w["te2.b"], e2, M=B, N=4 * mc, K=4 * mc, silu_out=True)
+        ea = torch.empty(B, self.emb_total, device=self.dev, dtype=torch.float32)
+        o.small_linear(e2, self.w["emb.w"], self.w["emb.b"], ea, M=B, N=self.emb_total, K=4 * mc)
+        return ea
+
+    def _new(self, *shape):
+        return torch.empty(*shape, device=self.dev, dtype=self.hdt)
+
+    def _res(self, blk, x, emb_all, gn_ws, out=None, out2=None):
+        """x: NHWC view [B,H,W,cin] (may be a concat buffer).  Returns [B,H,W,cout]."""
+        o, w, p = self.ops, self.w, blk.prefix
+        B, H, W_, cin = x.shape
+        cout = blk.cout
+        a1 = self._new(B, H, W_, cin)
+        o.groupnorm(x, w[p + ".in_layers.0.g"], w[p + ".in_layers.0.b"], a1, B=B, HW=H * W_, C_=cin, eps=1e-5,
+                    silu=True, workspace=gn_ws, ldx=x.stride(2))
+        h1 = self._new(B, H, W_, cout)
+        off = self.emb_off[p]
+        o.gemm(a1, w[p + ".conv1.w"], h1, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cin),
+               rowvec=emb_all[:, off:off + cout])
+        a2 = self._new(B, H, W_, cout)
+        o.groupnorm(h1, w[p + ".out_layers.0.g"], w[p + ".out_layers.0.b"], a2, B=B, HW=H * W_, C_=cout, eps=1e-5,
+                    silu=True, workspace=gn_ws)
+        if out is None:
+            out = self._new(B, H, W_, cout)
+        if cin != cout:
+            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout), a_extra=x,
+                   ld_extra=x.stride(2), bias=w[p + ".conv2.b"], out2=out2)
+        else:
+            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout),
+                   bias=w[p + ".conv2.b"], residual=x, out2=out2)
+        return out
+
+    def _attn(self, blk, x, ctxc, gn_ws, out=None, out2=None):
+        o, w, p = self.ops, self.w, blk.prefix
+        B, H, W_, c = x.shape
+        heads, dh = self.cfg.heads_for(c)
+        inner = heads * dh
+        N, M = H * W_, B * H * W_
+        xn = self._new(B, H, W_, c)
+        o.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], xn, B=B, HW=N, C_=c, eps=1e-6, silu=False,
+                    workspace=gn_ws, ldx=x.stride(2))
+        t0 = o.gemm(xn.view(M, c), w[p + ".proj_in.w"], bias=w[p + ".proj_in.b"])
+        n1 = self._new(M, inner)
+        o.layernorm(t0, w[p + ".norm1.g"], w[p + ".norm1.b"], n1, M=M, C_=inner)
+        qkv = o.gemm(n1, w[p + ".qkv1.w"])                       # [M, 3*inner]
+        ao = self._new(M, inner)
+        o.attention(qkv, qkv[:, inner:], qkv[:, 2 * inner:], ao, B=B, heads=heads, Nq=N, Nkv=N, d=dh,
+                    q_strides=(N * 3 * inner, 3 * inner), k_strides=(N * 3 * inner, 3 * inner),
+                    v_strides=(N * 3 * inner, 3 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
+        t1 = o.gemm(ao, w[p + ".o1.w"], bias=w[p + ".o1.b"], residual=t0)
+        n2 = self._new(M, inner)
+        o.layernorm(t1, w[p + ".norm2.g"], w[p + ".norm2.b"], n2, M=M, C_=inner)
+        q2 = o.gemm(n2, w[p + ".q2.w"])
+        kv = ctxc["kv"][p]
+        Lc = ctxc["L"]
+        ao2 = self._new(M, inner)
+        o.attention(q2, kv, kv[:, inner:], ao2, B=B, heads=heads, Nq=N, Nkv=Lc, d=dh,
+                    q_strides=(N * inner, inner), k_strides=(Lc * 2 * inner, 2 * inner),
+                    v_strides=(Lc * 2 * inner, 2 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
+        t2 = o.gemm(ao2, w[p + ".o2.w"], bias=w[p + ".o2.b"], residual=t1)
+        n3 = self._new(M, inner)
+        o.layernorm(t2, w[p + ".norm3.g"], w[p + ".norm3.b"], n3, M=M, C_=inner)
+        g = o.gemm(n3, w[p + ".ff1.w"], bias=w[p + ".ff1.b"], act=L.EA_ACT_GEGLU)   # [M, 4*inner]
+        t3 = o.gemm(g, w[p + ".ff2.w"], bias=w[p + ".ff2.b"], residual=t2)
+        if out is None:
+            out = self._new(B, H, W_, c)
+        o.gemm(t3, w[p + ".proj_out.w"], out.view(M, -1) if out.is_contiguous() else out, M=M, bias=w[p + ".proj_out.b"],
+               residual=x, ldr=x.stride(2), ldo=out.stride(2), out2=out2,
+               ldo2=(out2.stride(2) if out2 is not None else None))
+        return out
+
+    def _run_layers(self, layers, h, emb_all, ctxc, gn_ws, final_out=None, final_out2=None):
+        """Run one TimestepEmbedSequential; the LAST operator writes to final_out / final_out2."""
+        o, w = self.ops, self.w
+        for i, blk in enumerate(layers):
+            last = i == len(layers) - 1
+            fo = final_out if last else None
+            fo2 = final_out2 if last else None
+            B, H, W_, _ = h.shape
+            if blk.kind == "res":
+                h = self._res(blk, h, emb_all, gn_ws, out=fo, out2=fo2)
+            elif blk.kind == "attn":
+                h = self._attn(blk, h, ctxc, gn_ws, out=fo, out2=fo2)
+            elif blk.kind == "down":
+                out = fo if fo is not None else self._new(B, H // 2, W_ // 2, blk.cout)
+                o.gemm(h, w[blk.prefix + ".w"], out, mode=L.EA_GEMM_CONV_S2, conv=(B, H // 2, W_ // 2, blk.cin),
+                       bias=w[blk.prefix + ".b"], out2=fo2)
+                h = out
+            elif blk.kind == "up":
+                up = self._new(B, 2 * H, 2 * W_, blk.cin)
+                o.upsample2x(h, up, B=B, H=H, W=W_, C_=blk.cin)
+                out = fo if fo is not None else self._new(B, 2 * H, 2 * W_, blk.cout)
+                o.gemm(up, w[blk.prefix + ".w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, 2 * H, 2 * W_, blk.cin),
+                       bias=w[blk.prefix + ".b"], out2=fo2)
+                h = out
+            else:
+                raise ValueError(blk.kind)
+        return h
+
+
+class UNetRunner:
+    """One denoising-step network: UNet + k ControlNets sharing skip-concat buffers."""
+
+    def __init__(self, unet: PackedNet, controlnets, device):
+        self.unet, self.cns, self.dev = unet, list(controlnets), device
+        self.ops = unet.ops
+        self.hdt = unet.hdt
+
+    def _encoder(self, net: PackedNet, x_half, emb_all, ctxc, gn_ws, guided_hint=None, sinks=None, scale=1.0):
+        """Runs input_blocks + middle.  For the UNet (`sinks` is a dict of concat slots) each skip is
+        dual-stored into its decoder concat slot; for a ControlNet each zero-conv accumulates
+        `scale * zero_conv(h)` into the slot instead of materialising the residual."""
+        o, w, topo = net.ops, net.w, net.topo
+        B, H, W_, _ = x_half.shape
+        is_unet = net.kind == "unet"
+        h = None
+        for i, layers in enumerate(topo.input_blocks):
+            slot = sinks["skip"][i]
+            if layers[0].kind == "conv_in":
+                blk = layers[0]
+                h = net._new(B, H, W_, blk.cout)
+                o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], h, B=B, Hin=H, Win=W_,
+                              Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, add=guided_hint)
+                if is_unet:
+                    o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], slot, B=B, Hin=H, Win=W_,
+                                  Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, ldo=slot.stride(2))
+            else:
+                h = net._run_layers(layers, h, emb_all, ctxc, gn_ws, final_out2=slot if is_unet else None)
+            if not is_unet:
+                c = h.shape[-1]
+                M = h.shape[0] * h.shape[1] * h.shape[2]
+                p = f"zero_convs.{i}.0"
+                o.gemm(h.view(M, c), w[p + ".w"], slot, M=M, bias=w[p + ".b"], out_scale=scale, accumulate=True,
+                       ldo=slot.stride(2))
+        mid_sink = sinks["mid"]
+        if is_unet:
+            h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws, final_out=mid_sink)
+        else:
+            h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws)
+            c = h.shape[-1]
+            M = h.shape[0] * h.shape[1] * h.shape[2]
+            o.gemm(h.view(M, c), w["mid_out.w"], mid_sink, M=M, bias=w["mid_out.b"], out_scale=scale,
+                   accumulate=True, ldo=mid_sink.stride(2))
+        return h
+
+    def alloc_sinks(self, B, H, W_):
+        """Skip-concat buffers of the decoder: cat_i = [h (C1) | skip_i + control_i (C2)]."""
+        topo = self.unet.topo
+        chans = list(topo.input_chans)
+        sizes = []  # spatial size of each skip
+        hh, ww = H, W_
+        for layers in topo.input_blocks:
+            if layers[0].kind == "down":
+                hh, ww = hh // 2, ww // 2
+            sizes.append((hh, ww))
+        cats, skip_slots = [], [None] * len(chans)
+        for oi, layers in enumerate(topo.output_blocks):
+            si = len(chans) - 1 - oi
+            c2 = chans[si]
+            c1 = layers[0].cin - c2
+            sh, sw = sizes[si]
+            cat = torch.empty(B, sh, sw, c1 + c2, device=self.dev, dtype=self.hdt)
+            cats.append((cat, c1))
+            skip_slots[si] = cat[..., c1:]
+        mh, mw = sizes[-1]
+        mid = cats[0][0][..., :cats[0][1]]  # mid output IS the h-part of the first decoder concat
+        return {"cats": cats, "skip": skip_slots, "mid": mid}
+
+    def eps_features(self, x_half, t_dev, ctx_cache, hints, scales, gn_ws=None):
+        """Runs UNet encoder, ControlNets, UNet decoder; returns the GroupNorm+SiLU'd input of the
+        final convolution [B,H,W,mc] (the out conv itself is fused with CFG/DDIM)."""
+        un = self.unet
+        o = self.ops
+        B, H, W_, _ = x_half.shape
+        if gn_ws is None:
+            gn_ws = torch.empty(B * 32 * 2, device=self.dev, dtype=torch.float32)
+        sinks = self.alloc_sinks(B, H, W_)
+        emb_u = un._emb(t_dev, B)
+        self._encoder(un, x_half, emb_u, ctx_cache[0], gn_ws, sinks=sinks)
+        for k, cn in enumerate(self.cns):
+            emb_c = cn._emb(t_dev, B)
+            self._encoder(cn, x_half, emb_c, ctx_cache[1 + k], gn_ws, guided_hint=hints[k], sinks=sinks,
+                          scale=float(scales[k]))
+        topo = un.topo
+        cats = sinks["cats"]
+        h = None
+        for oi, layers in enumerate(topo.output_blocks):
+            cat, c1 = cats[oi]
+            if oi + 1 < len(cats):
+                nxt, n1 = cats[oi + 1]
+                dst = nxt[..., :n1]
+            else:
+                dst = None
+            h = un._run_layers(layers, cat, emb_u, ctx_cache[0], gn_ws, final_out=dst)
+        mc = un.cfg.model_channels
+        xn = un._new(B, H, W_, mc)
+        o.groupnorm(h, un.w["out.g"], un.w["out.b"], xn, B=B, HW=H * W_, C_=mc, eps=1e-5, silu=True,
+                    workspace=gn_ws, ldx=h.stride(2))
+        return xn

@@ -134,11 +134,11 @@ def layernorm(x, gamma, beta, out, *, M, C_, eps=1e-5, ldx=None, ldo=None):
     return out
 
 
-def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, silu=False, add=None):
+def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, silu=False, add=None, ldo=0):
     """w: fp32 [k, k, Cin, Cout]."""
     lib = L.lib()
     L.check(lib.ea_conv_direct(_p(x), _p(w), _p(bias), _p(out), B, Hin, Win, Cin, Cout, ksize, stride,
-                               1 if silu else 0, _p(add), _stream()), "ea_conv_direct")
+                               1 if silu else 0, _p(add), ldo, _stream()), "ea_conv_direct")
     return out
 
 

@@ -140,9 +140,10 @@ int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* 
 
 /* ---- small / memory-bound operators -------------------------------------------------------
  * ea_conv_direct: generic small 3x3 / 1x1 conv on CUDA cores (NHWC half, fp32 weights
- *   [Cout, kh, kw, Cin]), pad = ksize/2, stride 1 or 2, optional SiLU.  Used for the ControlNet
- *   hint stack (cldm/cldm.py:147-163), conv_in 4->320 (openaimodel.py:533-539) and the SAM
- *   patch embedding when expressed as a GEMM prologue.
+ *   [kh, kw, Cin, Cout]), pad = ksize/2, stride 1 or 2, optional SiLU, optional dense half `add`
+ *   tensor (ControlNet: h = conv_in(x) + guided_hint, cldm/cldm.py:293-297), output pixel stride
+ *   ldo (0 -> Cout).  Used for the ControlNet hint stack (cldm/cldm.py:147-163) and conv_in
+ *   4->320 (openaimodel.py:533-539).
  * ea_upsample2x: nearest x2 on NHWC (openaimodel.py:110-116).
  * ea_small_linear: y[M<=16, N] = act_out( W[N,K] * act_in(x[M,K]) + b ), fp32 in/out, half
  *   weights; time_embed and ResBlock.emb_layers (openaimodel.py:526-531,204-210).
@@ -150,7 +151,7 @@ int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* 
  */
 int ea_conv_direct(const void* x, const float* w, const float* bias, void* out, int B, int Hin,
                    int Win, int Cin, int Cout, int ksize, int stride, int silu,
-                   const void* add, void* stream);
+                   const void* add, long long ldo, void* stream);
 int ea_upsample2x(const void* x, void* out, int B, int H, int W, int C, void* stream);
 int ea_small_linear(const float* x, const void* w, const float* bias, float* y, int M, int N,
                     int K, int silu_in, int silu_out, void* stream);

@@ -1,0 +1,165 @@
+"""Torch/CPU emulation of editanything_b200.ops — TEST INFRASTRUCTURE ONLY.
+
+Lets the `-m "not gpu"` suite exercise the host-side graph logic (weight packing, skip-concat
+sinks, zero-conv accumulation, GEGLU interleave, fused-skip K extension ...) of
+editanything_b200.nets against the oracle without a GPU.  It is injected explicitly by the tests
+(`PackedNet(..., backend=cpu_ops)`); the product never selects it.
+"""
+import torch
+import torch.nn.functional as F
+
+EA_GEMM_LINEAR, EA_GEMM_CONV_S1, EA_GEMM_CONV_S2 = 0, 1, 2
+EA_ACT_NONE, EA_ACT_SILU, EA_ACT_GELU, EA_ACT_GEGLU = 0, 1, 2, 3
+_count = 0
+
+
+def half_dtype():
+    return torch.float32
+
+
+def launch_count():
+    return _count
+
+
+def _bump(n=1):
+    global _count
+    _count += n
+
+
+def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, conv=None, a_extra=None,
+         bias=None, rowvec=None, rows_per_batch=0, residual=None, out2=None, out_f32=None, act=0,
+         out_scale=1.0, accumulate=False, ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0,
+         force_stages=0):
+    _bump()
+    Nn = w.shape[0]
+    if mode == EA_GEMM_LINEAR:
+        A = a.reshape(-1, a.shape[-1]).float()
+        y = A @ w.float().t()
+        batch_rows = rows_per_batch
+    else:
+        B, H, W_, Cin = conv
+        x = a.float().permute(0, 3, 1, 2)
+        wm = w[:, :9 * Cin].float().reshape(Nn, 3, 3, Cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x, wm, stride=1 if mode == EA_GEMM_CONV_S1 else 2, padding=1)
+        if a_extra is not None:
+            ce = a_extra.shape[-1]
+            y = y + F.conv2d(a_extra.float().permute(0, 3, 1, 2), w[:, 9 * Cin:9 * Cin + ce].float().reshape(Nn, ce, 1, 1))
+        y = y.permute(0, 2, 3, 1).reshape(B * H * W_, Nn)
+        batch_rows = H * W_
+    if bias is not None:
+        y = y + bias
+    if rowvec is not None:
+        nb = y.shape[0] // batch_rows if batch_rows else 1
+        y = y + (rowvec.repeat_interleave(batch_rows, 0) if batch_rows else rowvec[:1])
+    if act == EA_ACT_SILU:
+        y = F.silu(y)
+    elif act == EA_ACT_GELU:
+        y = F.gelu(y)
+    elif act == EA_ACT_GEGLU:
+        y = y.reshape(y.shape[0], Nn // 128, 2, 64)
+        y = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(y.shape[0], Nn // 2)
+    y = y * out_scale
+    if residual is not None:
+        y = y + residual.reshape(y.shape).float()
+    tgt = out if out is not None else out_f32
+    if tgt is None:
+        tgt = torch.empty(y.shape, dtype=half_dtype())
+    if accumulate:
+        y = y + tgt.reshape(y.shape).float()
+    tgt.copy_(y.reshape(tgt.shape))
+    if out2 is not None:
+        out2.copy_(y.reshape(out2.shape))
+    return tgt
+
+
+def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_strides, o_strides, scale,
+              rel_h=None, rel_w=None, rel_s=0):
+    _bump()
+
+    def view(t, N, st):
+        return torch.as_strided(t, (B, N, heads, d), (st[0], st[1], d, 1), t.storage_offset()).float()
+
+    qf = view(q, Nq, q_strides).permute(0, 2, 1, 3)
+    kf = view(k, Nkv, k_strides).permute(0, 2, 1, 3)
+    vf = view(v, Nkv, v_strides).permute(0, 2, 1, 3)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if rel_h is not None:
+        bias = rel_h.reshape(B, heads, Nq, rel_s, 1) + rel_w.reshape(B, heads, Nq, 1, rel_s)
+        s = s + bias.reshape(B, heads, Nq, rel_s * rel_s)[..., :Nkv]
+    o = (s.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    torch.as_strided(out, (B, Nq, heads * d), (o_strides[0], o_strides[1], 1), out.storage_offset()).copy_(o)
+    return out
+
+
+def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True, workspace=None, x2=None,
+              C1=0, ldx=None, ldx2=None, ldo=None):
+    _bump(2)
+    xs = x.reshape(B, HW, -1).float()
+    if x2 is not None:
+        xs = torch.cat([xs, x2.reshape(B, HW, -1).float()], -1)
+    y = F.group_norm(xs.permute(0, 2, 1), groups, gamma, beta, eps).permute(0, 2, 1)
+    if silu:
+        y = F.silu(y)
+    out.copy_(y.reshape(out.shape))
+    return out
+
+
+def layernorm(x, gamma, beta, out, *, M, C_, eps=1e-5, ldx=None, ldo=None):
+    _bump()
+    out.copy_(F.layer_norm(x.float().reshape(M, C_), (C_,), gamma, beta, eps).reshape(out.shape))
+    return out
+
+
+def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, silu=False, add=None, ldo=0):
+    _bump()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, stride=stride, padding=ksize // 2)
+    if silu:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    out.copy_(y)
+    return out
+
+
+def upsample2x(x, out, *, B, H, W, C_):
+    _bump()
+    out.copy_(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1))
+    return out
+
+
+def small_linear(x, w, bias, y, *, M, N, K, silu_in=False, silu_out=False):
+    _bump()
+    xx = F.silu(x) if silu_in else x
+    r = xx @ w.float().t()
+    if bias is not None:
+        r = r + bias
+    y.copy_(F.silu(r) if silu_out else r)
+    return y
+
+
+def timestep_embedding(t, out, *, B, dim):
+    _bump()
+    half = dim // 2
+    freqs = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    out.copy_(torch.cat([torch.cos(args), torch.sin(args)], -1))
+    return out
+
+
+def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, mask=None,
+                 lat_half_out=None, Nimg, H, W, C_):
+    _bump()
+    eps = F.conv2d(xn.float().permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    if eps_out is not None:
+        eps_out.copy_(eps)
+    if latents is not None:
+        e = eps[:Nimg] + guidance * (eps[Nimg:] - eps[:Nimg])
+        sa, s1a, sap, s1ap = [float(c) for c in coef]
+        x0 = (latents - s1a * e) / sa
+        xp = sap * x0 + s1ap * e
+        if known is not None:
+            xp = known * mask[..., None] + xp * (1 - mask[..., None])
+        latents.copy_(xp)
+        if lat_half_out is not None:
+            lat_half_out.copy_(torch.cat([xp, xp]))
