@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on B200: 512x512 50-step SAM+ControlNet-inpaint images/sec and
+the fused ControlNet x2 + UNet + CFG + DDIM step time.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): SD1.5 topology, 512x512 image -> 64x64 latents, 1 image per
+GPU + classifier-free guidance (B = 2), SAM-ControlNet + inpaint-ControlNet, 77-token context,
+DDIM eta = 0; synthetic inputs and seeded random weights (no checkpoints / network here).
+A "step" is one denoising step.  `value` (images/s) = n_gpus / (50 * step + SAM encode), both
+components device-timed in this run and reported in `config`.
+One process per GPU; images shard one per GPU (weak scaling) with a single NCCL all-gather of the
+final latents/images at the end — no data-path collective inside the step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STEP_TFLOP = 2.740        # algorithmic 2*MAC per fused step at configs[1] (BASELINE.md §2)
+SAM_TFLOP = 5.96          # SAM ViT-H image encoder, one 1024x1024 image (BASELINE.md §2)
+DDIM_STEPS = 50
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1442.5), d.get("bf16_tflops", 1682.0), d.get("hbm_gbs", 6585.4), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max([int(s[1]) for s in self.samples if s[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def make_inputs(cfg, B, lat, L, seed):
+    """Same synthetic inputs as oracle/inputs.py (SURVEY.md §8d); duplicated here so the product arm
+    imports nothing from oracle/."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cfg.in_channels, lat, lat, generator=g)
+    ctx = torch.randn(B, L, cfg.context_dim, generator=g)
+    h0 = torch.randint(0, 256, (1, 3, 8 * lat, 8 * lat), generator=g).float()
+    h0[:, 2] = 0
+    h1 = torch.rand(1, 3, 8 * lat, 8 * lat, generator=g)
+    q = 2 * lat
+    h1[:, :, q:8 * lat - q, q:8 * lat - q] = -1.0
+    return x, ctx, [h0.repeat(B, 1, 1, 1), h1.repeat(B, 1, 1, 1)]
+
+
+class GemmProbe:
+    """Wraps editanything_b200.ops to time every ea_gemm launch with CUDA events on the launching
+    stream and count its algorithmic FLOPs (roofline of the dominant kernel)."""
+
+    def __init__(self, ops):
+        self._ops, self.records = ops, []
+
+    def __getattr__(self, n):
+        return getattr(self._ops, n)
+
+    def gemm(self, a, w, out=None, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = self._ops.gemm(a, w, out, **kw)
+        e1.record()
+        conv = kw.get("conv")
+        M = conv[0] * conv[1] * conv[2] if conv else (kw.get("M") or a.shape[0])
+        self.records.append((e0, e1, 2.0 * M * w.shape[0] * w.shape[1]))
+        return r
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from editanything_b200 import ops
+    from editanything_b200.denoise import DenoiseEngine, ddim_schedule
+    from editanything_b200.unet_spec import SD15, make_state_dict
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    cfg = SD15
+    sust, burst, hbm, peak_src = _peaks()
+
+    usd = make_state_dict(cfg, "unet", 101, device=dev)
+    csds = [make_state_dict(cfg, "controlnet", 102, device=dev), make_state_dict(cfg, "controlnet", 103, device=dev)]
+    eng = DenoiseEngine(cfg, usd, csds, dev)
+    del usd, csds
+    torch.cuda.empty_cache()
+    x, ctx, hints = make_inputs(cfg, 2, 64, 77, 11 + rank)
+    ts, a, ap = ddim_schedule(DDIM_STEPS)
+
+    # ---- device-resident timed region: exactly K denoising steps --------------------------------
+    eng.prepare(ctx, hints, [0.5, 1.0])
+    eng.begin(x[:1], guidance=9.0, use_graph=not args.no_graph)
+    for i in range(args.warmup):
+        eng.step(int(ts[i % DDIM_STEPS]), float(a[i % DDIM_STEPS]), float(ap[i % DDIM_STEPS]))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        j = (args.warmup + i) % DDIM_STEPS
+        eng.step(int(ts[j]), float(a[j]), float(ap[j]))
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    launches_per_step = getattr(eng, "launches_per_step", None)
+    if launches_per_step is None:
+        launches_per_step = ops.launch_count() // max(1, args.steps)
+    finite = bool(torch.isfinite(eng.latents()).all().item())
+
+    # ---- SAM ViT-H encoder (once per image) -----------------------------------------------------
+    sam_ms, sam_note = None, "not built yet: images/s below is denoise-only"
+    try:
+        from editanything_b200.sam import SamEncoderEngine, make_sam_state_dict, SAM_VIT_H
+        ssd = make_sam_state_dict(SAM_VIT_H, 201, device=dev)
+        sam = SamEncoderEngine(SAM_VIT_H, ssd, dev)
+        del ssd
+        img = torch.randn(1, 3, 1024, 1024, device=dev)
+        for _ in range(2):
+            sam.encode(img)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            sam.encode(img)
+        s1.record()
+        torch.cuda.synchronize()
+        sam_ms = s0.elapsed_time(s1) / 3
+        sam_note = "SAM ViT-H 1024x1024 encode, device-timed, 3 iterations"
+    except ImportError:
+        pass
+
+    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0)
+    value = world * 1000.0 / img_ms
+
+    # ---- roofline of the dominant kernel (ea_gemm_kernel), live CUDA events ----------------------
+    probe = GemmProbe(ops)
+    eng_ops_saved = (eng.ops, eng.runner.ops, eng.unet.ops, [c.ops for c in eng.cns])
+    eng.ops = eng.runner.ops = eng.unet.ops = probe
+    for c in eng.cns:
+        c.ops = probe
+    eng._use_graph = False
+    j = (args.warmup + args.steps) % DDIM_STEPS
+    eng.step(int(ts[j]), float(a[j]), float(ap[j]))
+    probe.records.clear()
+    eng.step(int(ts[j]), float(a[j]), float(ap[j]))
+    torch.cuda.synchronize()
+    g_ms = sum(r[0].elapsed_time(r[1]) for r in probe.records)
+    g_fl = sum(r[2] for r in probe.records)
+    n_gemm = len(probe.records)
+    eng.ops, eng.runner.ops, eng.unet.ops = eng_ops_saved[0], eng_ops_saved[1], eng_ops_saved[2]
+    for c, o in zip(eng.cns, eng_ops_saved[3]):
+        c.ops = o
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "ea_gemm_kernel", "achieved": round(achieved, 1), "peak": sust,
+                "unit": "TFLOP/s", "frac": round(achieved / sust, 4), "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches": n_gemm, "gemm_ms_per_step": round(g_ms, 3),
+                "gemm_tflop_per_step": round(g_fl / 1e12, 3),
+                "whole_step": {"tflop": STEP_TFLOP, "achieved": round(STEP_TFLOP / (ms_step * 1e-3), 1),
+                               "frac": round(STEP_TFLOP / (ms_step * 1e-3) / sust, 4)}}
+
+    # ---- e2e: host buffers in, host result out, through the public engine API ---------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        hx, hctx = x[:1].pin_memory(), ctx.pin_memory()
+        hh = [h.pin_memory() for h in hints]
+        n_img = 2
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_img):
+            eng.prepare(hctx.to(dev, non_blocking=True), [h.to(dev, non_blocking=True) for h in hh], [0.5, 1.0])
+            eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
+            for i in range(DDIM_STEPS):
+                eng.step(int(ts[i]), float(a[i]), float(ap[i]))
+            res = eng.latents().cpu()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+            gathered = [torch.empty_like(res).to(dev) for _ in range(world)]
+            dist.all_gather(gathered, res.to(dev))   # the single end-of-job collective
+        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh)) * 4
+        e2e = {"value": round(world * n_img / dt, 4), "unit": "images/s",
+               "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": res.numel() * 4 // DDIM_STEPS,
+               "note": "engine API: pinned host ctx/hints/latents -> H2D -> prepare (ctx K/V, hint stack) -> 50 fused "
+                       "steps -> D2H latents; SAM/VAE not included"}
+
+    line = {
+        "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
+        "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 storage / fp32 accumulate" if ops.half_dtype() == torch.float16 else "bf16 storage / fp32 accumulate",
+        "data": "synthetic inputs, seeded random weights (SD1.5 topology, 859.5M + 2x361.3M params)",
+        "config": {"workload": "BASELINE.json configs[1]: SD1.5 ControlNet-inpaint 512x512, 50 DDIM steps, batch=1/GPU "
+                               "(+CFG => B=2), SAM+inpaint ControlNets, L=77",
+                   "global_batch": world, "parallelism": f"dp{world} (one image per GPU, final all-gather)",
+                   "l2": "weights touched per step (3.16 GB) exceed the 126 MB L2; no explicit flush",
+                   "cuda_graph": not args.no_graph, "sam_ms_per_image": sam_ms, "sam": sam_note,
+                   "image_ms": round(img_ms, 3), "outputs_finite": finite},
+        "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
+        "clocks": clocks, "roofline": roofline, "e2e": e2e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def _oracle_step_fn(cfg):
+    """Builds the CPU oracle step (ControlNet x2 -> UNet -> CFG -> DDIM) at configs[1] size."""
+    from editanything_b200.unet_spec import build_topology, make_state_dict
+    from oracle import unet_oracle as O
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    usd = {k: v.cpu() for k, v in make_state_dict(cfg, "unet", 101, device=dev).items()}
+    csds = [{k: v.cpu() for k, v in make_state_dict(cfg, "controlnet", s, device=dev).items()} for s in (102, 103)]
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    x, ctx, hints = make_inputs(cfg, 2, 64, 77, 11)
+    ts, a, ap = O.make_ddim_schedule(DDIM_STEPS)
+    state = {"lat": x[:1].clone(), "i": len(ts) - 1}
+
+    def step():
+        i = state["i"]
+        xx = torch.cat([state["lat"], state["lat"]])
+        with torch.no_grad():
+            e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], xx, torch.full((2,), int(ts[i])), ctx, hints, [0.5, 1.0])
+        state["lat"], _ = O.ddim_step(state["lat"], e[:1], e[1:], 9.0, float(a[i]), float(ap[i]))
+        state["i"] = i - 1 if i > 0 else len(ts) - 1
+    return step
+
+
+def cpu_baseline(sample_steps=1):
+    from editanything_b200.unet_spec import SD15
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = _oracle_step_fn(SD15)
+    step()  # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        step()
+    dt = (time.perf_counter() - t0) / sample_steps
+    return {"value": round(1.0 / (DDIM_STEPS * dt), 6), "unit": "images/s", "cores": cores, "kind": "port",
+            "ms_per_step": round(dt * 1e3, 1),
+            "sample": f"{sample_steps} full-size fused step(s) (2 ControlNets + UNet + CFG + DDIM, B=2, 64x64, fp32) of the "
+                      f"oracle port on {cores} host threads after 1 warm-up; images/s = 1/(50*step), denoise only"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own algorithm (oracle port of its ldm/cldm modules; the
+    reference is pure Python and cannot travel to the box) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from editanything_b200.unet_spec import SD15
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = _oracle_step_fn(SD15)
+    budget_s = 240.0
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    n_w = max(0, min(args.warmup - 1, int(budget_s * 0.2 / max(first, 1e-3))))
+    for _ in range(n_w):
+        step()
+    k = max(1, min(args.steps, int(budget_s * 0.8 / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    v = round(1.0 / (DDIM_STEPS * dt), 6)
+    sample = (f"{k} of the requested {args.steps} steps timed (each a full-size configs[1] fused step on CPU, fp32, "
+              f"{cores} threads; bounded to ~{int(budget_s)} s); images/s = 1/(50*step), denoise only")
+    line = {"impl": "reference",
+            "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
+            "value": v, "unit": "images/s", "n_gpus": world, "steps": k, "warmup": 1 + n_w,
+            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic inputs, seeded random weights",
+            "config": {"workload": "BASELINE.json configs[1] on host CPU (reference ldm/cldm algorithm, oracle port)"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -191,24 +191,24 @@ def param_shapes(cfg: UNetConfig, kind: str):
     return P
 
 
-def make_state_dict(cfg: UNetConfig, kind: str, seed: int, dtype=torch.float32):
+def make_state_dict(cfg: UNetConfig, kind: str, seed: int, dtype=torch.float32, device="cpu"):
     """Deterministic synthetic weights (CPU generator).  Weights ~ N(0, 1/fan_in) so activations
     keep O(1) scale through the network; the reference's zero-initialised tensors
     (zero_module: openaimodel.py:228-231,729; attention.py:312-318; cldm/cldm.py:162,282) are drawn
     like every other weight — with them at zero every golden vector would be identically 0."""
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
     for name, (shape, role) in param_shapes(cfg, kind).items():
         if role == "w":
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+            t = torch.randn(shape, generator=g, device=device) * (fan_in ** -0.5)
         elif role == "b":
-            t = torch.randn(shape, generator=g) * 0.05
+            t = torch.randn(shape, generator=g, device=device) * 0.05
         elif role == "g":
-            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
         else:
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * torch.randn(shape, generator=g, device=device)
         sd[name] = t.to(dtype)
     return sd
