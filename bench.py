@@ -136,12 +136,16 @@ def run_ours(args, rank, world, local_rank):
     ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if args.profiler_range:
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: capture the timed region only
     e0.record()
     for i in range(args.steps):
         j = (args.warmup + i) % DDIM_STEPS
         eng.step(int(ts[j]), float(a[j]), float(ap[j]))
     e1.record()
     torch.cuda.synchronize()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
@@ -159,6 +163,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- SAM ViT-H encoder (once per image) -----------------------------------------------------
     sam_ms, sam_note = None, "not built yet: images/s below is denoise-only"
     try:
+        if args.no_sam:
+            raise ImportError("skipped")
         from editanything_b200.sam import SamEncoderEngine, make_sam_state_dict, SAM_VIT_H
         ssd = make_sam_state_dict(SAM_VIT_H, 201, device=dev)
         sam = SamEncoderEngine(SAM_VIT_H, ssd, dev)
@@ -210,7 +216,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: host buffers in, host result out, through the public engine API ---------------------
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         hx, hctx = x[:1].pin_memory(), ctx.pin_memory()
         hh = [h.pin_memory() for h in hints]
         n_img = 2
@@ -281,9 +287,24 @@ def _oracle_step_fn(cfg):
     return step
 
 
+def usable_cores():
+    """Host threads this process may actually run on: the scheduler affinity mask capped by the
+    cgroup CPU quota (a 128-thread box that grants the container fewer CPUs thrashes when torch
+    spawns one thread per logical CPU: 151 s/step measured vs 12.8 s on 8 dedicated cores), and by
+    64, beyond which the oracle's small-batch convolutions stop scaling."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(sample_steps=1):
     from editanything_b200.unet_spec import SD15
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     step = _oracle_step_fn(SD15)
     step()  # warm-up (allocator, thread pool)
@@ -303,7 +324,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from editanything_b200.unet_spec import SD15
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     step = _oracle_step_fn(SD15)
     budget_s = 240.0
@@ -340,6 +361,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--no-sam", action="store_true", help="profiling runs only: skip the SAM encoder leg")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu): skip the e2e leg")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -76,6 +76,8 @@ SYMBOLS = {
     "ea_sam_relpos": (_I, [_P, _L, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ea_window_partition": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_window_unpartition": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ea_sam_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "ea_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

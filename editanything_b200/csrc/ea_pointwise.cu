@@ -437,6 +437,52 @@ __global__ void window_unpartition_kernel(const ea_half* __restrict__ xw,
   }
 }
 
+// Patch embedding im2col (SAM PatchEmbed: Conv2d(3, C, k=16, s=16)): fp32 NCHW image ->
+// half [B*gh*gw, Cin*ps*ps] with K index = (c*ps + kh)*ps + kw, i.e. the flattened conv weight
+// order, so the convolution is one ea_gemm.  Thread <-> 8 consecutive kw.
+__global__ void patchify_kernel(const float* __restrict__ img, ea_half* __restrict__ out, int B,
+                                int Cin, int H, int W, int ps) {
+  const int gh = H / ps, gw = W / ps;
+  const int K = Cin * ps * ps;
+  const int kvec = K >> 3;
+  const long long total = (long long)B * gh * gw * kvec;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int kv = (int)(idx % kvec);
+    long long patch = idx / kvec;
+    int pw = (int)(patch % gw);
+    int ph = (int)((patch / gw) % gh);
+    int b = (int)(patch / ((long long)gw * gh));
+    int k = kv << 3;
+    int kw = k % ps;
+    int kh = (k / ps) % ps;
+    int c = k / (ps * ps);
+    const float* src = img + (((long long)b * Cin + c) * H + (ph * ps + kh)) * W + pw * ps + kw;
+    float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    float4 b4 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    uint4 o = make_uint4(ea_pack2(a.x, a.y), ea_pack2(a.z, a.w), ea_pack2(b4.x, b4.y),
+                         ea_pack2(b4.z, b4.w));
+    *reinterpret_cast<uint4*>(out + patch * K + k) = o;
+  }
+}
+
+// NHWC half -> NCHW fp32 (the layout/precision the reference hands to the prompt/mask decoder).
+__global__ void nhwc_to_nchw_f32_kernel(const ea_half* __restrict__ x, float* __restrict__ out,
+                                        int B, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = ea_h2f(x[((long long)b * HW + p) * C + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) out[((long long)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = 148LL * 16;
@@ -573,5 +619,23 @@ extern "C" int ea_window_unpartition(const void* xw, const void* residual, void*
   window_unpartition_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
       reinterpret_cast<const ea_half*>(xw), reinterpret_cast<const ea_half*>(residual),
       reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh, nWw);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_sam_patchify(const float* img, void* out, int B, int Cin, int H, int W, int ps,
+                               void* stream) {
+  if (!img || !out) return EA_ERR_ARG;
+  if (ps % 8 != 0 || H % ps != 0 || W % ps != 0 || W % 4 != 0) return EA_ERR_SHAPE;
+  long long total = (long long)B * (H / ps) * (W / ps) * (Cin * ps * ps / 8);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
+      img, reinterpret_cast<ea_half*>(out), B, Cin, H, W, ps);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_nhwc_to_nchw_f32(const void* x, float* out, int B, int HW, int C, void* stream) {
+  if (!x || !out) return EA_ERR_ARG;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nhwc_to_nchw_f32_kernel<<<grid, block, 0, EA_STREAM(stream)>>>(
+      reinterpret_cast<const ea_half*>(x), out, B, HW, C);
   return EA_LAUNCH_OK();
 }

@@ -186,3 +186,15 @@ def window_unpartition(xw, residual, out, *, B, H, W, C_, ws):
     L.check(lib.ea_window_unpartition(_p(xw), _p(residual), _p(out), B, H, W, C_, ws, _stream()),
             "ea_window_unpartition")
     return out
+
+
+def sam_patchify(img, out, *, B, Cin, H, W, ps):
+    lib = L.lib()
+    L.check(lib.ea_sam_patchify(_p(img), _p(out), B, Cin, H, W, ps, _stream()), "ea_sam_patchify")
+    return out
+
+
+def nhwc_to_nchw_f32(x, out, *, B, HW, C_):
+    lib = L.lib()
+    L.check(lib.ea_nhwc_to_nchw_f32(_p(x), _p(out), B, HW, C_, _stream()), "ea_nhwc_to_nchw_f32")
+    return out

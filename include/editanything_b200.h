@@ -188,6 +188,14 @@ int ea_window_partition(const void* x, void* out, int B, int H, int W, int C, in
                         void* stream);
 int ea_window_unpartition(const void* xw, const void* residual, void* out, int B, int H, int W,
                           int C, int ws, void* stream);
+/* ea_sam_patchify: im2col of PatchEmbed's Conv2d(3, C, kernel = stride = ps) (segment_anything
+ *   image_encoder PatchEmbed; HF modeling_sam.py:97-129): fp32 NCHW [B,Cin,H,W] ->
+ *   half [B*(H/ps)*(W/ps), Cin*ps*ps], K index = (c*ps + kh)*ps + kw (flattened conv weight).
+ * ea_nhwc_to_nchw_f32: half NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (image-embedding layout handed
+ *   to the mask decoder). */
+int ea_sam_patchify(const float* img, void* out, int B, int Cin, int H, int W, int ps,
+                    void* stream);
+int ea_nhwc_to_nchw_f32(const void* x, float* out, int B, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, con
         batch_rows = rows_per_batch
     else:
         B, H, W_, Cin = conv
-        x = a.float().permute(0, 3, 1, 2)
+        x = a.float().reshape(B, -1, a.shape[-2] if a.dim() == 4 else (W_ if mode == EA_GEMM_CONV_S1 else 2 * W_), Cin).permute(0, 3, 1, 2)
         wm = w[:, :9 * Cin].float().reshape(Nn, 3, 3, Cin).permute(0, 3, 1, 2)
         y = F.conv2d(x, wm, stride=1 if mode == EA_GEMM_CONV_S1 else 2, padding=1)
         if a_extra is not None:
@@ -163,3 +163,43 @@ def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance
         latents.copy_(xp)
         if lat_half_out is not None:
             lat_half_out.copy_(torch.cat([xp, xp]))
+
+
+# ------------------------------------------------------------------ SAM helpers
+def sam_relpos(q, q_bs, q_ns, Rh, Rw, rel_h, rel_w, *, B, heads, S, d):
+    _bump()
+    qf = torch.as_strided(q, (B, S * S, heads, d), (q_bs, q_ns, d, 1), q.storage_offset()).float()
+    qf = qf.permute(0, 2, 1, 3).reshape(B * heads, S, S, d)
+    rel_h.copy_(torch.einsum("bhwc,hkc->bhwk", qf, Rh).reshape(rel_h.shape))
+    rel_w.copy_(torch.einsum("bhwc,wkc->bhwk", qf, Rw).reshape(rel_w.shape))
+
+
+def window_partition(x, out, *, B, H, W, C_, ws):
+    _bump()
+    nWh, nWw = (H + ws - 1) // ws, (W + ws - 1) // ws
+    xp = F.pad(x.reshape(B, H, W, C_), (0, 0, 0, nWw * ws - W, 0, nWh * ws - H))
+    out.copy_(xp.view(B, nWh, ws, nWw, ws, C_).permute(0, 1, 3, 2, 4, 5).reshape(out.shape))
+    return out
+
+
+def window_unpartition(xw, residual, out, *, B, H, W, C_, ws):
+    _bump()
+    nWh, nWw = (H + ws - 1) // ws, (W + ws - 1) // ws
+    x = xw.reshape(B, nWh, nWw, ws, ws, C_).permute(0, 1, 3, 2, 4, 5).reshape(B, nWh * ws, nWw * ws, C_)[:, :H, :W]
+    if residual is not None:
+        x = x + residual.reshape(B, H, W, C_)
+    out.copy_(x.reshape(out.shape))
+    return out
+
+
+def sam_patchify(img, out, *, B, Cin, H, W, ps):
+    _bump()
+    cols = F.unfold(img.float(), kernel_size=ps, stride=ps)          # [B, Cin*ps*ps, L], K order (c, kh, kw)
+    out.copy_(cols.permute(0, 2, 1).reshape(out.shape))
+    return out
+
+
+def nhwc_to_nchw_f32(x, out, *, B, HW, C_):
+    _bump()
+    out.copy_(x.float().reshape(B, HW, C_).permute(0, 2, 1).reshape(out.shape))
+    return out
