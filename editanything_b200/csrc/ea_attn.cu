@@ -5,17 +5,22 @@
 // _ATTN_PRECISION="fp32" path) and SAM's windowed / global attention with decomposed relative
 // position bias.  The N x N logits never touch HBM.
 //
-// One CTA = one (batch, head, 128-query tile); 192 threads:
-//   warp 0    TMA producer: Q once, then K/V tiles of 128 keys into a 1-2 stage ring.  Head
-//             dims that are not a multiple of 64 (40, 80, 160) are zero-padded for free by TMA
-//             out-of-bounds fill: the tensor map's innermost extent is d, the box is 64 wide.
-//   warp 1    TMEM allocator + MMA issuer: S = Q K^T (M=128, N=128, K=d) into TMEM columns
-//             [0,128); O += P V (M=128, N=d, K=128) into columns [128,128+d); V is consumed as
-//             an MN-major B operand straight from its row-major [key, d] tile.
-//   warps 2-5 softmax: thread <-> query row.  tcgen05.ld the logits, online softmax in fp32
-//             (exp2 with folded scale, lazy rescale of O in TMEM only when the running max
-//             moves by more than 2^8), P written to shared memory as the K-major SWIZZLE_128B
-//             A operand of the second MMA.  Final 1/l normalisation and 16-byte stores.
+// One CTA = one (batch, head) and NQT query tiles of 128 rows (NQT = 2: two tiles ping-pong so
+// the tensor core works on one tile's MMAs while the other tile is in softmax; NQT = 1: one
+// tile with a double-buffered logits accumulator).  Warp roles (128 + 128*NQT threads, 1 CTA/SM):
+//   warp 0     TMA producer: Q tiles once, then K/V tiles of 128 keys into a `stages`-deep ring.
+//              Head dims that are not a multiple of 64 (40, 80, 160) are zero-padded for free by
+//              TMA out-of-bounds fill (tensor-map inner extent d, box 64 wide).
+//   warp 1     TMEM allocator + MMA issuer (one lane): S = Q K^T (M=128, N=128, K=d) into TMEM;
+//              O += P V (M=128, N=d, K=128) with P read straight from TMEM (tcgen05.mma A operand
+//              in tensor memory) and V consumed as an MN-major B operand from its row-major tile.
+//   warps 4..  softmax warpgroups, thread <-> query row: tcgen05.ld the logits, two passes
+//              (row max, then exp2 with the folded scale), P packed to 16-bit and written back over
+//              the logits' own TMEM columns (tcgen05.st); O is rescaled in TMEM only when the
+//              running max moves by more than 2^8 (exact: the final 1/l uses the same max).
+//              Final 1/l normalisation and 16-byte stores.
+// TMEM map (512 columns): NQT=2: S_A 0, S_B 128, O_A 256, O_B 384;  NQT=1: S[0] 0, S[1] 128, O 256.
+#include <stdlib.h>
 #include "ea_common.cuh"
 #include "ea_internal.h"
 
@@ -24,7 +29,7 @@ namespace ea {
 static constexpr int AT_BQ = 128;
 static constexpr int AT_BKV = 128;
 static constexpr int AT_ATOM = 128 * 128;  // bytes of one 128-row x 64-half swizzled atom
-static constexpr int AT_THREADS = 192;
+static constexpr int AT_MAX_STAGES = 4;
 
 struct AttnKParams {
   int Nq, Nkv, d, heads;
@@ -32,7 +37,7 @@ struct AttnKParams {
   int ksteps;  // ceil(d / 16) MMA K-steps for Q K^T
   int dpad16;  // d rounded up to 16: MMA N of the PV product
   int stages;
-  int tmem_cols;
+  int p_smem;  // 1: stage P through shared memory (SS MMA) instead of TMEM (testing fallback)
   float scale_log2;
   ea_half* out;
   long long o_bs, o_ns;
@@ -41,29 +46,40 @@ struct AttnKParams {
   int rel_s;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st16_half(uint32_t taddr, const uint32_t (&r)[16]) {
+  tmem_st16(taddr, r);
+}
+
+template <int NQT, bool BIAS>
+__global__ void __launch_bounds__(128 + 128 * NQT, 1)
 ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  // layout: Q[nd] | P[2] | stages x (K[nd] | V[nd]) | barriers
+  // layout: Q[NQT][nd] | KV[stages][K nd | V nd] | P[NQT][2] (only if p_smem) | barriers
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + p.nd * AT_ATOM;
-  uint8_t* sKV = sP + 2 * AT_ATOM;
+  uint8_t* sKV = sQ + NQT * p.nd * AT_ATOM;
   const int kv_stage_bytes = 2 * p.nd * AT_ATOM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.stages * kv_stage_bytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_final = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sP = sKV + p.stages * kv_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (p.p_smem ? NQT * 2 * AT_ATOM : 0));
+  uint64_t* q_full = bars;                      // [1]
+  uint64_t* kv_full = bars + 1;                 // [AT_MAX_STAGES]
+  uint64_t* kv_empty = kv_full + AT_MAX_STAGES; // [AT_MAX_STAGES]
+  uint64_t* s_full = kv_empty + AT_MAX_STAGES;  // [2]  NQT=2: per tile; NQT=1: per S buffer
+  uint64_t* p_ready = s_full + 2;               // [2]  per tile
+  uint64_t* pv_done = p_ready + 2;              // [2]  per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Nkv + AT_BKV - 1) / AT_BKV;
 
   if (warp == 0 && lane == 0) {
@@ -71,29 +87,31 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < AT_MAX_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_final, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_ready[t], 128);
+      mbar_init(&pv_done[t], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      mbar_expect_tx(q_full, (uint32_t)(p.nd * AT_ATOM));
-      for (int a = 0; a < p.nd; ++a)
-        tma_load_4d(sQ + a * AT_ATOM, &tmQ, q_full, a * 64, head, qt * AT_BQ, b);
+      mbar_expect_tx(q_full, (uint32_t)(NQT * p.nd * AT_ATOM));
+      for (int t = 0; t < NQT; ++t)
+        for (int a = 0; a < p.nd; ++a)
+          tma_load_4d(sQ + (t * p.nd + a) * AT_ATOM, &tmQ, q_full, a * 64, head,
+                      (qb * NQT + t) * AT_BQ, b);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -113,139 +131,253 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc(128, 128, 0, 0);
       const uint32_t idesc_o = umma_idesc(128, (uint32_t)p.dpad16, 0, 1);  // B (=V) MN-major
-      mbar_wait(q_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&kv_full[stage], phase);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + stage * kv_stage_bytes);
-        const uint32_t aV = aK + p.nd * AT_ATOM;
-        const uint32_t aQ = smem_u32(sQ);
-        // S = Q K^T
+      const uint32_t aQ = smem_u32(sQ);
+      const uint32_t aKV = smem_u32(sKV);
+      const uint32_t aP = smem_u32(sP);
+      // S_t(j) = Q_t K_j^T into TMEM columns s_col
+      auto issue_S = [&](int t, int stage, uint32_t s_col) {
+        const uint32_t q0 = aQ + (uint32_t)(t * p.nd * AT_ATOM);
+        const uint32_t k0 = aKV + (uint32_t)(stage * kv_stage_bytes);
         for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t off = (uint32_t)((ks >> 2) * AT_ATOM + (ks & 3) * 32);
-          umma_f16_ss(tmem_S, umma_desc_k_sw128(aQ + off, 1024), umma_desc_k_sw128(aK + off, 1024),
-                      idesc_s, ks > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + s_col, umma_desc_k_sw128(q0 + off, 1024),
+                      umma_desc_k_sw128(k0 + off, 1024), idesc_s, ks > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        // O += P V   (after the softmax warps published P for this tile)
-        mbar_wait(p_full, (uint32_t)(j & 1));
-        tc_fence_after();
-        const uint32_t aP = smem_u32(sP);
+      };
+      // O_t += P_t(j) V_j ; P lives in TMEM columns p_col (16-bit pairs) or in smem tile t
+      auto issue_PV = [&](int t, int stage, uint32_t p_col, uint32_t o_col, bool first) {
+        const uint32_t v0 = aKV + (uint32_t)(stage * kv_stage_bytes + p.nd * AT_ATOM);
         for (int ks = 0; ks < AT_BKV / 16; ++ks) {
-          const uint32_t offP = (uint32_t)((ks >> 2) * AT_ATOM + (ks & 3) * 32);
-          const uint32_t offV = (uint32_t)(ks * 16 * 128);  // 16 key rows of 128 B
-          umma_f16_ss(tmem_O, umma_desc_k_sw128(aP + offP, 1024),
-                      umma_desc_mn_sw128(aV + offV, AT_ATOM, 1024), idesc_o,
-                      (j > 0 || ks > 0) ? 1u : 0u);
+          const uint64_t dV = umma_desc_mn_sw128(v0 + (uint32_t)(ks * 16 * 128), AT_ATOM, 1024);
+          const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
+          if (p.p_smem) {
+            const uint32_t offP =
+                (uint32_t)(t * 2 * AT_ATOM + (ks >> 2) * AT_ATOM + (ks & 3) * 32);
+            umma_f16_ss(tmem_base + o_col, umma_desc_k_sw128(aP + offP, 1024), dV, idesc_o, acc);
+          } else {
+            umma_f16_ts(tmem_base + o_col, tmem_base + p_col + (uint32_t)(ks * 8), dV, idesc_o,
+                        acc);
+          }
         }
-        umma_commit(&kv_empty[stage]);
-        if (j == n_tiles - 1) umma_commit(o_final);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else {
-    // ======================= softmax / correction / epilogue ==============
-    const int wq = warp & 3;  // TMEM lane quarter accessible to this warp
-    const int r = wq * 32 + lane;
-    const int q = qt * AT_BQ + r;
-    const bool row_ok = q < p.Nq;
-    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    const float LOG2E = 1.4426950408889634f;
-    const long long bh = (long long)b * p.heads + head;
-    const float* rh = p.rel_h ? p.rel_h + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s : nullptr;
-    const float* rw = p.rel_w ? p.rel_w + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s : nullptr;
-    float m_used = -INFINITY;
-    float l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, (uint32_t)(j & 1));
-      tc_fence_after();
-      const int kv_left = p.Nkv - j * AT_BKV;  // valid keys in this tile (>= 1)
-      // pass 1: row max
-      float m_tile = -INFINITY;
-      for (int c = 0; c < AT_BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (rh) {
-            int kk = j * AT_BKV + c + i;
-            if (kk < p.Nkv) {
-              int kh = kk / p.rel_s;
-              t += (__ldg(rh + kh) + __ldg(rw + (kk - kh * p.rel_s))) * LOG2E;
+      };
+      mbar_wait(q_full, 0);
+      if (NQT == 2) {
+        // stage/phase of K/V tile j
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_S(0, 0, 0);
+        umma_commit(&s_full[0]);
+        issue_S(1, 0, 128);
+        umma_commit(&s_full[1]);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+          const bool more = j + 1 < n_tiles;
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&p_ready[t], (uint32_t)(j & 1));
+            tc_fence_after();
+            issue_PV(t, stage, (uint32_t)(t * 128), (uint32_t)(256 + t * 128), j == 0);
+            umma_commit(&pv_done[t]);
+            if (t == 1) umma_commit(&kv_empty[stage]);
+            if (more) {
+              if (t == 0) {
+                mbar_wait(&kv_full[nstage], nphase);
+                tc_fence_after();
+              }
+              issue_S(t, nstage, (uint32_t)(t * 128));
+              umma_commit(&s_full[t]);
             }
           }
-          if (c + i < kv_left) m_tile = fmaxf(m_tile, t);
+          stage = nstage;
+          phase = nphase;
+        }
+      } else {
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_S(0, 0, 0);
+        umma_commit(&s_full[0]);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+          const bool more = j + 1 < n_tiles;
+          const uint32_t nbuf = (uint32_t)((j + 1) & 1) * 128u;
+          if (more && p.stages > 1) {  // next logits tile while this one is in softmax
+            mbar_wait(&kv_full[nstage], nphase);
+            tc_fence_after();
+            issue_S(0, nstage, nbuf);
+            umma_commit(&s_full[(j + 1) & 1]);
+          }
+          mbar_wait(&p_ready[0], (uint32_t)(j & 1));
+          tc_fence_after();
+          issue_PV(0, stage, (uint32_t)(j & 1) * 128u, 256u, j == 0);
+          umma_commit(&pv_done[0]);
+          umma_commit(&kv_empty[stage]);
+          if (more && p.stages == 1) {
+            mbar_wait(&kv_full[nstage], nphase);
+            tc_fence_after();
+            issue_S(0, nstage, nbuf);
+            umma_commit(&s_full[(j + 1) & 1]);
+          }
+          stage = nstage;
+          phase = nphase;
         }
       }
-      // lazy rescale (exact: the final normalisation uses the same m_used)
+    }
+  } else if (warp >= 4) {
+    // ======================= softmax / correction / epilogue ==============
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int wq = warp & 3;        // TMEM lane quarter accessible to this warp
+    const int r = wq * 32 + lane;
+    const int q = (qb * NQT + t) * AT_BQ + r;
+    const bool row_ok = q < p.Nq;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t tmem_O = tmem_base + lane_off + (NQT == 2 ? (uint32_t)(256 + t * 128) : 256u);
+    const float LOG2E = 1.4426950408889634f;
+    const float* rh = nullptr;
+    const float* rw = nullptr;
+    if (BIAS) {
+      const long long bh = (long long)b * p.heads + head;
+      rh = p.rel_h + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s;
+      rw = p.rel_w + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s;
+    }
+    float m_run = -INFINITY;  // running max in the scaled log2 domain
+    float l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = (NQT == 2) ? t : (j & 1);
+      const uint32_t sph = (NQT == 2) ? (uint32_t)(j & 1) : (uint32_t)((j >> 1) & 1);
+      mbar_wait(&s_full[sb], sph);
+      tc_fence_after();
+      const uint32_t tmem_S = tmem_base + lane_off + (uint32_t)sb * 128u;
+      const int valid = min(AT_BKV, p.Nkv - j * AT_BKV);  // keys of this tile that exist (>= 1)
+      // ---- pass 1: row max of the scaled logits
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < AT_BKV; c += 32) {
+        if (c >= valid) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_S + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (BIAS) {
+          int kk = j * AT_BKV + c;
+          int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
+          float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float tt = fmaf(__uint_as_float(v[i]), p.scale_log2,
+                            fmaf(__ldg(rw + kw), LOG2E, bh_));
+            if (c + i < valid) mx = fmaxf(mx, tt);
+            if (++kw == p.rel_s) { kw = 0; ++kh; bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E; }
+          }
+        } else if (c + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      const float m_tile = BIAS ? mx : mx * p.scale_log2;  // scale > 0
+      // ---- lazy rescale of the running state
       float alpha = 1.f;
-      bool need = (m_tile > m_used + 8.f);
+      const bool need = m_tile > m_run + 8.f;
       if (need) {
-        alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_tile);
-        m_used = m_tile;
+        alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile (m_run = -inf)
+        m_run = m_tile;
         l *= alpha;
       }
-      const bool warp_need = __any_sync(0xffffffffu, need) && (j > 0);
-      if (warp_need) {
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
+        tc_fence_after();
+#pragma unroll 1
         for (int c = 0; c < p.dpad16; c += 16) {
           uint32_t o[16];
-          tmem_ld16(tmem_O + lane_off + (uint32_t)c, o);
+          tmem_ld16(tmem_O + (uint32_t)c, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tmem_O + lane_off + (uint32_t)c, o);
+          tmem_st16(tmem_O + (uint32_t)c, o);
         }
         tmem_st_wait();
       }
-      // pass 2: P = exp2(t - m_used), row sum, write swizzled K-major tile
+      // ---- pass 2: P = exp2(s * scale - m_run), row sum, publish P
+      const float neg_m = -m_run;
+#pragma unroll 1
       for (int c = 0; c < AT_BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
-        float pv[32];
+        uint32_t pk[16];
+        if (c < valid) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + (uint32_t)c, v);
+          tmem_ld_wait();
+          float e[32];
+          if (BIAS) {
+            int kk = j * AT_BKV + c;
+            int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
+            float bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(v[i]) * p.scale_log2;
-          if (rh) {
-            int kk = j * AT_BKV + c + i;
-            if (kk < p.Nkv) {
-              int kh = kk / p.rel_s;
-              t += (__ldg(rh + kh) + __ldg(rw + (kk - kh * p.rel_s))) * LOG2E;
+            for (int i = 0; i < 32; ++i) {
+              float tt = fmaf(__uint_as_float(v[i]), p.scale_log2,
+                              fmaf(__ldg(rw + kw), LOG2E, bh_));
+              e[i] = (c + i < valid) ? ex2_approx(tt) : 0.f;
+              if (++kw == p.rel_s) {
+                kw = 0; ++kh;
+                bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
+              }
             }
-          }
-          float e = (c + i < kv_left) ? exp2f(t - m_used) : 0.f;
-          pv[i] = e;
-          l += e;
-        }
-        const int atom = c >> 6;
-        uint8_t* prow = sP + atom * AT_ATOM + r * 128;
+          } else if (c + 32 <= valid) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          int c16 = ((c & 63) >> 3) + g;
-          uint4 o = make_uint4(ea_pack2(pv[g * 8 + 0], pv[g * 8 + 1]),
-                               ea_pack2(pv[g * 8 + 2], pv[g * 8 + 3]),
-                               ea_pack2(pv[g * 8 + 4], pv[g * 8 + 5]),
-                               ea_pack2(pv[g * 8 + 6], pv[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) = o;
+            for (int i = 0; i < 32; ++i)
+              e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              e[i] = (c + i < valid)
+                         ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m))
+                         : 0.f;
+          }
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
+          l += (s0 + s1) + (s2 + s3);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = ea_pack2(e[2 * i], e[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        if (p.p_smem) {
+          uint8_t* prow = sP + (t * 2 + (c >> 6)) * AT_ATOM + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c16 = ((c & 63) >> 3) + g;
+            *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          }
+        } else {
+          tmem_st16(tmem_S + (uint32_t)(c >> 1), pk);  // P over the consumed logits columns
         }
       }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
+      if (p.p_smem) fence_proxy_async();
+      else tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_ready[t]);
     }
-    // epilogue
-    mbar_wait(o_final, 0);
+    // ---- epilogue: O / l
+    mbar_wait(&pv_done[t], (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
     const float inv_l = 1.f / l;
     ea_half* orow = p.out + (long long)b * p.o_bs + (long long)(row_ok ? q : 0) * p.o_ns +
                     (long long)head * p.d;
+#pragma unroll 1
     for (int c = 0; c < p.dpad16; c += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_O + lane_off + (uint32_t)c, o);
+      tmem_ld16(tmem_O + (uint32_t)c, o);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -268,7 +400,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -283,6 +415,20 @@ static int encode_qkv(CUtensorMap* m, const void* base, int d, int heads, int N,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int NQT, bool BIAS>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnKParams& p, dim3 grid, int smem_bytes, cudaStream_t stream) {
+  static int max_set = 0;
+  if (smem_bytes > max_set) {
+    if (cudaFuncSetAttribute(ea_attn_kernel<NQT, BIAS>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return EA_ERR_CUDA;
+    max_set = smem_bytes;
+  }
+  ea_attn_kernel<NQT, BIAS><<<grid, 128 + 128 * NQT, smem_bytes, stream>>>(tq, tk, tv, p);
+  return 0;
 }
 
 }  // namespace ea
@@ -300,35 +446,57 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   if ((a->rel_h != nullptr) != (a->rel_w != nullptr)) return EA_ERR_ARG;
   if (a->rel_h && a->rel_s <= 0) return EA_ERR_ARG;
 
+  static const int force_p_smem = [] { const char* e = getenv("EA_ATTN_P_SMEM"); return e && e[0] == '1'; }();
+  static const int force_nqt = [] { const char* e = getenv("EA_ATTN_NQT"); return e ? atoi(e) : 0; }();
+
   AttnKParams p;
   memset(&p, 0, sizeof(p));
   p.Nq = a->Nq; p.Nkv = a->Nkv; p.d = a->d; p.heads = a->heads;
   p.nd = (a->d + 63) / 64;
   p.ksteps = (a->d + 15) / 16;
   p.dpad16 = p.ksteps * 16;
-  p.stages = p.nd <= 2 ? 2 : 1;
-  p.tmem_cols = (128 + p.nd * 64) <= 256 ? 256 : 512;
+  p.p_smem = force_p_smem;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<ea_half*>(a->out);
   p.o_bs = a->o_bs; p.o_ns = a->o_ns;
   p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.rel_s = a->rel_s;
+
+  // two query tiles per CTA when both accumulators fit TMEM (d <= 128) and there is a second tile
+  int nqt = (a->Nq > AT_BQ && p.dpad16 <= 128) ? 2 : 1;
+  if (force_nqt == 1 || force_nqt == 2) nqt = (force_nqt == 2 && p.dpad16 > 128) ? 1 : force_nqt;
+  const int budget = 225 * 1024 - 1024 - 256;
+  const int fixed = nqt * p.nd * AT_ATOM + (p.p_smem ? nqt * 2 * AT_ATOM : 0);
+  int stages = (budget - fixed) / (2 * p.nd * AT_ATOM);
+  if (stages > AT_MAX_STAGES) stages = AT_MAX_STAGES;
+  if (nqt == 2 && stages < 2) {  // the ping-pong schedule needs two K/V stages
+    nqt = 1;
+    const int fixed1 = p.nd * AT_ATOM + (p.p_smem ? 2 * AT_ATOM : 0);
+    stages = (budget - fixed1) / (2 * p.nd * AT_ATOM);
+    if (stages > AT_MAX_STAGES) stages = AT_MAX_STAGES;
+  }
+  if (stages < 1) return EA_ERR_SHAPE;
+  const int n_tiles = (a->Nkv + AT_BKV - 1) / AT_BKV;
+  if (stages > n_tiles) stages = n_tiles;
+  if (nqt == 2 && stages < 2) stages = 2;
+  p.stages = stages;
 
   CUtensorMap tq, tk, tv;
   if (encode_qkv(&tq, a->q, a->d, a->heads, a->Nq, a->B, a->q_ns, a->q_bs)) return EA_ERR_TMAP;
   if (encode_qkv(&tk, a->k, a->d, a->heads, a->Nkv, a->B, a->k_ns, a->k_bs)) return EA_ERR_TMAP;
   if (encode_qkv(&tv, a->v, a->d, a->heads, a->Nkv, a->B, a->v_ns, a->v_bs)) return EA_ERR_TMAP;
 
-  const int smem_bytes =
-      p.nd * AT_ATOM + 2 * AT_ATOM + p.stages * 2 * p.nd * AT_ATOM + 9 * 8 + 16 + 1024;
-  static int max_set = 0;
-  if (smem_bytes > max_set) {
-    if (cudaFuncSetAttribute(ea_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_bytes) != cudaSuccess)
-      return EA_ERR_CUDA;
-    max_set = smem_bytes;
-  }
-  dim3 grid((unsigned)((a->Nq + AT_BQ - 1) / AT_BQ), (unsigned)a->heads, (unsigned)a->B);
-  ea_attn_kernel<<<grid, AT_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  const int smem_bytes = nqt * p.nd * AT_ATOM + p.stages * 2 * p.nd * AT_ATOM +
+                         (p.p_smem ? nqt * 2 * AT_ATOM : 0) + (1 + 2 * AT_MAX_STAGES + 6) * 8 + 16 +
+                         1024;
+  dim3 grid((unsigned)((a->Nq + AT_BQ * nqt - 1) / (AT_BQ * nqt)), (unsigned)a->heads,
+            (unsigned)a->B);
+  int st;
+  const bool bias = a->rel_h != nullptr;
+  if (nqt == 2) st = bias ? launch_attn<2, true>(tq, tk, tv, p, grid, smem_bytes, stream)
+                          : launch_attn<2, false>(tq, tk, tv, p, grid, smem_bytes, stream);
+  else st = bias ? launch_attn<1, true>(tq, tk, tv, p, grid, smem_bytes, stream)
+                 : launch_attn<1, false>(tq, tk, tv, p, grid, smem_bytes, stream);
+  if (st) return st;
   ea_count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : EA_ERR_CUDA;
 }
