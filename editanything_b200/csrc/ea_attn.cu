@@ -255,7 +255,82 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tmem_S = tmem_base + lane_off + (uint32_t)sb * 128u;
       const int valid = min(AT_BKV, p.Nkv - j * AT_BKV);  // keys of this tile that exist (>= 1)
-      // ---- pass 1: row max of the scaled logits
+      if (!BIAS) {
+        // ---- whole 128-column logits row in registers: ONE TMEM round trip per tile
+        uint32_t v[4][32];
+        tmem_ld32(tmem_S, v[0]);
+        tmem_ld32(tmem_S + 32u, v[1]);
+        tmem_ld32(tmem_S + 64u, v[2]);
+        tmem_ld32(tmem_S + 96u, v[3]);
+        tmem_ld_wait();
+        if (valid < AT_BKV) {  // last, partial K/V tile: keys that do not exist get -inf
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (h * 32 + i >= valid) v[h][i] = 0xff800000u;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(v[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[3][i]));
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0
+        float alpha = 1.f;
+        const bool need = m_tile > m_run + 8.f;
+        if (need) {
+          alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile (m_run = -inf)
+          m_run = m_tile;
+          l *= alpha;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < p.dpad16; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + (uint32_t)c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + (uint32_t)c, o);
+          }
+          tmem_st_wait();
+        }
+        const float neg_m = -m_run;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[h][i]), p.scale_log2, neg_m));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[h][i + 1]), p.scale_log2, neg_m));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(v[h][i + 2]), p.scale_log2, neg_m));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(v[h][i + 3]), p.scale_log2, neg_m));
+            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+            pk[i >> 1] = ea_pack2(e0, e1);
+            pk[(i >> 1) + 1] = ea_pack2(e2, e3);
+          }
+          if (p.p_smem) {
+            const int c = h * 32;
+            uint8_t* prow = sP + (t * 2 + (c >> 6)) * AT_ATOM + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int c16 = ((c & 63) >> 3) + g;
+              *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) =
+                  make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            }
+          } else {
+            tmem_st16(tmem_S + (uint32_t)(h * 16), pk);  // P over the consumed logits columns
+          }
+        }
+        l += (s0 + s1) + (s2 + s3);
+      } else {
+      // ---- BIAS (SAM rel-pos) path: two passes over TMEM, bias terms fetched per element
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < AT_BKV; c += 32) {
@@ -263,37 +338,26 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld32(tmem_S + (uint32_t)c, v);
         tmem_ld_wait();
-        if (BIAS) {
-          int kk = j * AT_BKV + c;
-          int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
-          float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
+        int kk = j * AT_BKV + c;
+        int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
+        float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float tt = fmaf(__uint_as_float(v[i]), p.scale_log2,
-                            fmaf(__ldg(rw + kw), LOG2E, bh_));
-            if (c + i < valid) mx = fmaxf(mx, tt);
-            if (++kw == p.rel_s) { kw = 0; ++kh; bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E; }
-          }
-        } else if (c + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          float tt = fmaf(__uint_as_float(v[i]), p.scale_log2, fmaf(__ldg(rw + kw), LOG2E, bh_));
+          if (c + i < valid) mx = fmaxf(mx, tt);
+          if (++kw == p.rel_s) { kw = 0; ++kh; bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E; }
         }
       }
-      const float m_tile = BIAS ? mx : mx * p.scale_log2;  // scale > 0
-      // ---- lazy rescale of the running state
+      const float m_tile = mx;
       float alpha = 1.f;
       const bool need = m_tile > m_run + 8.f;
       if (need) {
-        alpha = ex2_approx(m_run - m_tile);  // 0 on the first tile (m_run = -inf)
+        alpha = ex2_approx(m_run - m_tile);
         m_run = m_tile;
         l *= alpha;
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
+        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < p.dpad16; c += 16) {
@@ -306,7 +370,6 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         tmem_st_wait();
       }
-      // ---- pass 2: P = exp2(s * scale - m_run), row sum, publish P
       const float neg_m = -m_run;
 #pragma unroll 1
       for (int c = 0; c < AT_BKV; c += 32) {
@@ -316,30 +379,17 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld32(tmem_S + (uint32_t)c, v);
           tmem_ld_wait();
           float e[32];
-          if (BIAS) {
-            int kk = j * AT_BKV + c;
-            int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
-            float bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
+          int kk = j * AT_BKV + c;
+          int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
+          float bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float tt = fmaf(__uint_as_float(v[i]), p.scale_log2,
-                              fmaf(__ldg(rw + kw), LOG2E, bh_));
-              e[i] = (c + i < valid) ? ex2_approx(tt) : 0.f;
-              if (++kw == p.rel_s) {
-                kw = 0; ++kh;
-                bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
-              }
+          for (int i = 0; i < 32; ++i) {
+            float tt = fmaf(__uint_as_float(v[i]), p.scale_log2, fmaf(__ldg(rw + kw), LOG2E, bh_));
+            e[i] = (c + i < valid) ? ex2_approx(tt) : 0.f;
+            if (++kw == p.rel_s) {
+              kw = 0; ++kh;
+              bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
             }
-          } else if (c + 32 <= valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              e[i] = (c + i < valid)
-                         ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m))
-                         : 0.f;
           }
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -360,9 +410,10 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           }
         } else {
-          tmem_st16(tmem_S + (uint32_t)(c >> 1), pk);  // P over the consumed logits columns
+          tmem_st16(tmem_S + (uint32_t)(c >> 1), pk);
         }
       }
+      }  // BIAS
       if (p.p_smem) fence_proxy_async();
       else tmem_st_wait();
       tc_fence_before();
@@ -463,6 +514,10 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
 
   // two query tiles per CTA when both accumulators fit TMEM (d <= 128) and there is a second tile
   int nqt = (a->Nq > AT_BQ && p.dpad16 <= 128) ? 2 : 1;
+  {  // one tile per CTA fills the machine better while two-tile CTAs would leave SMs idle
+    const long long ctas2 = (long long)((a->Nq + 2 * AT_BQ - 1) / (2 * AT_BQ)) * a->heads * a->B;
+    if (nqt == 2 && ctas2 < 148) nqt = 1;
+  }
   if (force_nqt == 1 || force_nqt == 2) nqt = (force_nqt == 2 && p.dpad16 > 128) ? 1 : force_nqt;
   const int budget = 225 * 1024 - 1024 - 256;
   const int fixed = nqt * p.nd * AT_ATOM + (p.p_smem ? nqt * 2 * AT_ATOM : 0);

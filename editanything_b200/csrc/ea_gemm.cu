@@ -56,6 +56,11 @@ struct GemmKParams {
   int act;
   float out_scale;
   int accumulate;
+  // split-K: blockIdx.z = split index; partial tiles go through `ws`, arrival counters in `cnt`
+  int splits;
+  int kb_per_split;
+  float* ws;   // [tiles][splits][128][BN] fp32
+  int* cnt;    // [tiles][2]: arrived, done (zero between launches)
 };
 
 __device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n0, int& h0,
@@ -68,6 +73,167 @@ __device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n
   n0 = nb * p.bn;
   h0 = th * p.bh;
   w0 = (r - th * p.tiles_w) * p.bw;
+}
+
+struct RowInfo {
+  long long m;   // global output row
+  bool ok;
+  int batch;
+};
+
+__device__ __forceinline__ RowInfo row_info(const GemmKParams& p, int tm, int r) {
+  RowInfo ri;
+  if (p.mode == EA_GEMM_LINEAR) {
+    ri.m = (long long)tm * BM + r;
+    ri.ok = ri.m < p.M;
+    ri.batch = p.rows_per_batch > 0 ? (int)(ri.m / p.rows_per_batch) : 0;
+  } else {
+    int n0, h0, w0;
+    tile_origin(p, tm, n0, h0, w0);
+    int dn = r / (p.bw * p.bh);
+    int rr = r - dn * (p.bw * p.bh);
+    int dh = rr / p.bw;
+    int dw = rr - dh * p.bw;
+    int n = n0 + dn, h = h0 + dh, w = w0 + dw;
+    ri.ok = (n < p.Bsz) && (h < p.H) && (w < p.W);
+    ri.m = ((long long)n * p.H + h) * p.W + w;
+    ri.batch = n;
+  }
+  return ri;
+}
+
+// named barrier over the 128 epilogue threads (warps 4-7); barrier 0 is __syncthreads
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// f[0..32) = sum over splits of the fp32 partials (fixed order: deterministic)
+__device__ __forceinline__ void reduce_chunk32(const float* base, int splits, int split_stride,
+                                               float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(base + (size_t)s * split_stride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v = __ldcg(src + j);
+      f[4 * j] += v.x; f[4 * j + 1] += v.y; f[4 * j + 2] += v.z; f[4 * j + 3] += v.w;
+    }
+  }
+}
+
+// GEGLU: value chunk fx (tile columns c..c+31), gate chunk fg (tile columns BN/2+c..): out = x*gelu(g)
+__device__ __forceinline__ void epilogue_geglu32(const GemmKParams& p, const RowInfo& ri, int ncol0,
+                                                 int half_bn, int c, float (&fx)[32],
+                                                 float (&fg)[32]) {
+  const int nout0 = (ncol0 >> 1) + c;  // output column of element 0
+  if (!(ri.ok && nout0 < (p.N >> 1))) return;
+  uint32_t packed[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float x0 = fx[j], x1 = fx[j + 1], g0 = fg[j], g1 = fg[j + 1];
+    if (p.bias) {
+      x0 += __ldg(p.bias + ncol0 + c + j);
+      x1 += __ldg(p.bias + ncol0 + c + j + 1);
+      g0 += __ldg(p.bias + ncol0 + half_bn + c + j);
+      g1 += __ldg(p.bias + ncol0 + half_bn + c + j + 1);
+    }
+    packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out + ri.m * p.ldo + nout0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+}
+
+// +bias -> +rowvec -> act -> *scale -> +residual -> (+= out) -> store (and out2); 32 columns
+__device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const RowInfo& ri,
+                                                 int n_first, float (&f)[32]) {
+  if (!(ri.ok && n_first < p.N)) return;
+  const long long m = ri.m;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (n_first + j < p.N) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n_first + j));
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+  }
+  if (p.rowvec) {
+    const float* rv = p.rowvec + (long long)ri.batch * p.rowvec_ld + n_first;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (n_first + j < p.N) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+  }
+  if (p.act == EA_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+  } else if (p.act == EA_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+  }
+  if (p.out_scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+  }
+  if (p.residual) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n_first);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n_first + q * 8 < p.N) {
+        uint4 u = __ldg(rp + q);
+        float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z), d = ea_unpack2(u.w);
+        f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+        f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+      }
+    }
+  }
+  if (p.out_f32) {
+    float* dst = p.out_f32 + m * p.ldo + n_first;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (n_first + j < p.N) {
+        float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        if (p.accumulate) {
+          float4 old = *reinterpret_cast<float4*>(dst + j);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+    return;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + n_first);
+  if (p.accumulate) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n_first + q * 8 < p.N) {
+        uint4 u = dst[q];
+        float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z), d = ea_unpack2(u.w);
+        f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+        f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+      }
+    }
+  }
+  uint4* dst2 = p.out2 ? reinterpret_cast<uint4*>(p.out2 + m * p.ldo2 + n_first) : nullptr;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (n_first + q * 8 < p.N) {
+      uint4 o = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                           ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
+      dst[q] = o;
+      if (dst2) dst2[q] = o;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -91,7 +257,9 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int tm = blockIdx.x;
   const int tn = blockIdx.y;
-  const int nkb = p.nkb_main + p.nkb_extra;
+  const int nkb_total = p.nkb_main + p.nkb_extra;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(nkb_total, kb0 + p.kb_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -126,7 +294,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.mode != EA_GEMM_LINEAR) tile_origin(p, tm, n0, h0, w0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
@@ -162,7 +330,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t idesc = umma_idesc(BM, (uint32_t)p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         uint32_t sa = smem_u32(smem + stage * stage_bytes);
@@ -172,7 +340,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+                      (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -183,155 +351,95 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ============================== epilogue ==============================
     const int wq = warp - 4;             // TMEM lane quarter
     const int r = wq * 32 + lane;        // tile row owned by this thread
-    long long m;                         // global output row
-    bool row_ok;
-    int batch;
-    if (p.mode == EA_GEMM_LINEAR) {
-      m = (long long)tm * BM + r;
-      row_ok = m < p.M;
-      batch = p.rows_per_batch > 0 ? (int)(m / p.rows_per_batch) : 0;
-    } else {
-      int n0, h0, w0;
-      tile_origin(p, tm, n0, h0, w0);
-      int dn = r / (p.bw * p.bh);
-      int rr = r - dn * (p.bw * p.bh);
-      int dh = rr / p.bw;
-      int dw = rr - dh * p.bw;
-      int n = n0 + dn, h = h0 + dh, w = w0 + dw;
-      row_ok = (n < p.Bsz) && (h < p.H) && (w < p.W);
-      m = ((long long)n * p.H + h) * p.W + w;
-      batch = n;
-    }
+    const int et = threadIdx.x - 128;    // 0..127 among the epilogue threads
+    RowInfo ri = row_info(p, tm, r);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     const int ncol0 = tn * p.BN;
-    if (p.act == EA_ACT_GEGLU) {
-      // tile columns: [0, BN/2) = value half, [BN/2, BN) = gate half (weights pre-interleaved)
-      const int half_bn = p.BN >> 1;
-      for (int c = 0; c < half_bn; c += 32) {
-        uint32_t xv[32], gv[32];
-        tmem_ld32(taddr + (uint32_t)c, xv);
-        tmem_ld32(taddr + (uint32_t)(half_bn + c), gv);
-        tmem_ld_wait();
-        const int nout0 = (ncol0 >> 1) + c;  // output column of element 0
-        if (row_ok && nout0 < (p.N >> 1)) {
-        uint32_t packed[16];
+    const bool geglu = p.act == EA_ACT_GEGLU;
+    const int half_bn = p.BN >> 1;
+    if (p.splits == 1) {
+      if (geglu) {
+        // tile columns: [0, BN/2) = value half, [BN/2, BN) = gate half (weights pre-interleaved)
+        for (int c = 0; c < half_bn; c += 32) {
+          uint32_t xv[32], gv[32];
+          tmem_ld32(taddr + (uint32_t)c, xv);
+          tmem_ld32(taddr + (uint32_t)(half_bn + c), gv);
+          tmem_ld_wait();
+          float fx[32], fg[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
-          float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
-          if (p.bias) {
-            x0 += __ldg(p.bias + ncol0 + c + j);
-            x1 += __ldg(p.bias + ncol0 + c + j + 1);
-            g0 += __ldg(p.bias + ncol0 + half_bn + c + j);
-            g1 += __ldg(p.bias + ncol0 + half_bn + c + j + 1);
-          }
-          packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+          for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
+          epilogue_geglu32(p, ri, ncol0, half_bn, c, fx, fg);
+          __syncwarp();
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + nout0);
+      } else {
+        for (int c = 0; c < p.BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2],
-                              packed[4 * q + 3]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          epilogue_chunk32(p, ri, ncol0 + c, f);
+          __syncwarp();
         }
-        __syncwarp();
       }
     } else {
+      // ---- split-K: publish the fp32 partial tile, wait for the sibling splits, then every
+      //      split CTA reduces and finishes a 1/splits share of the tile's (row, 32-col) units.
+      const int tile_id = tn * gridDim.x + tm;
+      float* wtile = p.ws + (size_t)tile_id * p.splits * (BM * p.BN);
+      float* mine = wtile + (size_t)blockIdx.z * (BM * p.BN);
       for (int c = 0; c < p.BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
-        const int n_first = ncol0 + c;
-        if (row_ok && n_first < p.N) {
-        float f[32];
+        float4* dst = reinterpret_cast<float4*>(mine + (size_t)r * p.BN + c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n_first + j < p.N) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n_first + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
+        for (int j = 0; j < 8; ++j)
+          __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+      }
+      __threadfence();
+      epi_bar_sync();
+      int* cnt = p.cnt + 2 * tile_id;
+      if (et == 0) {
+        atomicAdd(cnt, 1);
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(cnt) < p.splits) {
+          __nanosleep(40);
+          if (++spins > (1u << 24)) { asm volatile("trap;"); }
         }
-        if (p.rowvec) {
-          const float* rv = p.rowvec + (long long)batch * p.rowvec_ld + n_first;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n_first + j < p.N) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(rv + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
-        }
-        if (p.act == EA_ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-        } else if (p.act == EA_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
-        }
-        if (p.out_scale != 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n_first);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n_first + q * 8 < p.N) {
-              uint4 u = __ldg(rp + q);
-              float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z),
-                     d = ea_unpack2(u.w);
-              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
-              f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
-            }
-          }
-        }
-        if (p.out_f32) {
-          float* dst = p.out_f32 + m * p.ldo + n_first;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n_first + j < p.N) {
-              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if (p.accumulate) {
-                float4 old = *reinterpret_cast<float4*>(dst + j);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = o;
-            }
-          }
+      }
+      epi_bar_sync();
+      __threadfence();
+      const int chunks = geglu ? (half_bn >> 5) : (p.BN >> 5);
+      const int units = BM * chunks;
+      const int u0 = (int)(((long long)units * blockIdx.z) / p.splits);
+      const int u1 = (int)(((long long)units * (blockIdx.z + 1)) / p.splits);
+      for (int u = u0 + et; u < u1; u += 128) {
+        const int rr = u & (BM - 1);
+        const int c = (u >> 7) << 5;
+        RowInfo r2 = row_info(p, tm, rr);
+        if (geglu) {
+          float fx[32], fg[32];
+          reduce_chunk32(wtile + (size_t)rr * p.BN + c, p.splits, BM * p.BN, fx);
+          reduce_chunk32(wtile + (size_t)rr * p.BN + half_bn + c, p.splits, BM * p.BN, fg);
+          epilogue_geglu32(p, r2, ncol0, half_bn, c, fx, fg);
         } else {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + n_first);
-        if (p.accumulate) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n_first + q * 8 < p.N) {
-              uint4 u = dst[q];
-              float2 a = ea_unpack2(u.x), b = ea_unpack2(u.y), cc = ea_unpack2(u.z),
-                     d = ea_unpack2(u.w);
-              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
-              f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
-            }
-          }
+          float f[32];
+          reduce_chunk32(wtile + (size_t)rr * p.BN + c, p.splits, BM * p.BN, f);
+          epilogue_chunk32(p, r2, ncol0 + c, f);
         }
-        uint4* dst2 = p.out2 ? reinterpret_cast<uint4*>(p.out2 + m * p.ldo2 + n_first) : nullptr;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (n_first + q * 8 < p.N) {
-            uint4 o = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]),
-                                 ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
-                                 ea_pack2(f[q * 8 + 4], f[q * 8 + 5]),
-                                 ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
-            dst[q] = o;
-            if (dst2) dst2[q] = o;
-          }
+      }
+      epi_bar_sync();
+      if (et == 0) {
+        int old = atomicAdd(cnt + 1, 1);
+        if (old == p.splits - 1) {  // last finisher: re-arm the counters for the next launch
+          cnt[0] = 0;
+          cnt[1] = 0;
         }
-        }  // half output
-        }  // row_ok
-        __syncwarp();
       }
     }
   }
@@ -381,18 +489,71 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
   bn = 128 / (bw * bh);
 }
 
-static int pick_bn(int M_tiles, int N, int act) {
-  if (act == EA_ACT_GEGLU) return 128;
-  // prefer 128; fall back to 64 when it wastes less / fills more SMs
-  if (N % 128 == 0) {
-    long tiles128 = (long)M_tiles * (N / 128);
-    if (tiles128 >= 148) return 128;
-    return 64;
+// ---- launch planner -------------------------------------------------------------------
+// Picks (BN, stages, CTAs/SM, split-K) for one problem from a small cycle model: per K-block a CTA
+// needs max(MMA time, its share of chip bandwidth, TMA latency / stages in flight); small-M layers
+// (8x8 / 16x16 latents: M = 128 / 512) are weight-streaming bound, so K is split across CTAs until
+// every SM has one deep pipeline, and the partial tiles are combined in-kernel (see the epilogue).
+struct GemmPlan { int BN, stages, splits, kbps, occ; double cost; };
+
+static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm) {
+  GemmPlan best = {0, 0, 1, nkb, 1, 1e30};
+  const int cands[4] = {256, 128, 64, 32};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int BN = cands[ci];
+    if (act == EA_ACT_GEGLU && (BN < 64 || N % BN != 0)) continue;
+    if (BN > 32 && N <= BN / 2) continue;  // more than half the tile would be padding
+    const int nt = (N + BN - 1) / BN;
+    const long long tiles = (long long)mt * nt;
+    const int stage_bytes = BM * BK * 2 + BN * BK * 2;
+    for (int occ = 2; occ >= 1; --occ) {
+      const int avail = (occ == 2 ? 111 : 224) * 1024 - 2048;
+      int st = avail / stage_bytes;
+      if (st > 8) st = 8;
+      if (st > nkb) st = nkb < 2 ? 2 : nkb;
+      if (st < 2 || (occ == 2 && st < 3 && nkb >= 3)) continue;
+      const long long slots = (long long)n_sm * occ;
+      for (int pass = 0; pass < 2; ++pass) {
+        int splits = 1, kbps = nkb;
+        if (pass == 1) {
+          if (tiles >= slots || nkb < 8) break;
+          int s_max = (int)(slots / tiles);
+          if (s_max > nkb / 4) s_max = nkb / 4;
+          if (s_max < 2) break;
+          kbps = (nkb + s_max - 1) / s_max;
+          splits = (nkb + kbps - 1) / kbps;  // every split owns at least one K-block
+          if (splits < 2) break;
+          if (tiles > 2048 || tiles * splits * (long long)(BM * BN) > ws_floats) break;
+        }
+        const long long ctas = tiles * splits;
+        const long long waves = (ctas + slots - 1) / slots;
+        const long long conc = ctas < slots ? ctas : slots;
+        const int per_sm = (int)((conc + n_sm - 1) / n_sm);
+        const double t_mma = 2.0 * BN * per_sm;
+        const double t_mem = (double)conc * stage_bytes / 4500.0;
+        const double t_lat = 1800.0 / st;
+        double t_kb = t_mma > t_mem ? t_mma : t_mem;
+        if (t_lat > t_kb) t_kb = t_lat;
+        double cost = (double)waves * (kbps * t_kb + 3500.0 + 8.0 * BN);
+        if (splits > 1) cost += 3000.0 + 40.0 * splits;
+        if (cost < best.cost) best = {BN, st, splits, kbps, occ, cost};
+      }
+    }
   }
-  if (N % 64 == 0) return 64;
-  if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  return 128;
+  return best;
+}
+
+static int g_n_sm = 0;
+static int sm_count() {
+  if (!g_n_sm) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_n_sm = n;
+    else
+      g_n_sm = 148;
+  }
+  return g_n_sm;
 }
 
 }  // namespace ea
@@ -488,9 +649,38 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       Ktot += a->Cin_extra;
     }
   }
-  p.BN = a->force_bn > 0 ? a->force_bn : pick_bn(m_tiles, a->N, a->act);
+  const int nkb = p.nkb_main + p.nkb_extra;
+  // workspace: [0, 64 KB) arrival counters (int, zero between launches), then fp32 partial tiles
+  const long long ws_floats =
+      (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count());
+  if (a->force_bn > 0 || a->force_stages > 0 || a->force_splits > 0) {
+    if (a->force_bn > 0) plan.BN = a->force_bn;
+    const int sb = BM * BK * 2 + plan.BN * BK * 2;
+    if (a->force_bn > 0) plan.stages = plan.BN <= 128 ? 3 : 4;
+    if (a->force_stages > 0) plan.stages = a->force_stages;
+    if (plan.stages * sb > 224 * 1024) plan.stages = 224 * 1024 / sb;
+    if (plan.stages > nkb) plan.stages = nkb < 2 ? 2 : nkb;
+    if (a->force_bn > 0 || a->force_splits > 0) { plan.splits = 1; plan.kbps = nkb; }
+    if (a->force_splits > 1) {
+      plan.kbps = (nkb + a->force_splits - 1) / a->force_splits;
+      plan.splits = (nkb + plan.kbps - 1) / plan.kbps;
+    }
+  }
+  p.BN = plan.BN;
   if (p.BN != 32 && p.BN != 64 && p.BN != 128 && p.BN != 256) return EA_ERR_ARG;
   if (a->act == EA_ACT_GEGLU && (a->N % p.BN != 0 || p.BN < 64)) return EA_ERR_SHAPE;
+  const int n_tiles = (a->N + p.BN - 1) / p.BN;
+  p.splits = plan.splits;
+  p.kb_per_split = plan.kbps;
+  if (p.splits > 1) {
+    const long long tiles = (long long)m_tiles * n_tiles;
+    if (!ws_floats || tiles > 8192 || tiles * p.splits * (long long)(BM * p.BN) > ws_floats ||
+        tiles * p.splits > 2LL * sm_count())
+      return EA_ERR_SHAPE;  // split CTAs wait for each other: they must all be resident
+    p.cnt = reinterpret_cast<int*>(a->workspace);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + 65536);
+  }
   const long long ldw = a->ldw > 0 ? a->ldw : Ktot;
   if (ldw % 8 != 0) return EA_ERR_SHAPE;
   if (encode_2d(&tmB, a->w, (uint64_t)Ktot, (uint64_t)a->N, (uint64_t)ldw * 2, BK,
@@ -498,10 +688,9 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
     return EA_ERR_TMAP;
 
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  int stages = a->force_stages > 0 ? a->force_stages : (p.BN <= 128 ? 3 : 4);
-  const int nkb = p.nkb_main + p.nkb_extra;
-  if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
+  int stages = plan.stages;
   if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   static int max_set = 0;
@@ -511,7 +700,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       return EA_ERR_CUDA;
     max_set = smem_bytes;
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)((a->N + p.BN - 1) / p.BN), 1);
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)p.splits);
   ea_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmAx,
                                                              tmB, p);
   ea_count_launch();

@@ -8,102 +8,140 @@
 namespace ea {
 
 // ------------------------------- GroupNorm ---------------------------------
-// Pass 1: per-(batch, group) sum / sum-of-squares.  A CTA owns a run of pixels of one image and
-// walks them with fully coalesced row reads (thread <-> 8-channel vector); group partials are
-// combined in shared memory and flushed with one atomicAdd pair per group per CTA.
-__global__ void gn_stats_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
-                                const ea_half* __restrict__ x2, long long ldx2, int HW, int C,
-                                int groups, int pix_per_cta, float* __restrict__ ws) {
-  extern __shared__ float sh[];  // [groups*2]
+// ONE launch: every CTA owns a run of pixels of one image, keeps it in shared memory, reduces its
+// per-group sum / sum-of-squares in registers (thread <-> fixed 8-channel vector, so no atomics in
+// the loop), publishes 2*groups partials with global atomics, waits on a per-image arrival counter
+// (all CTAs are resident: grid <= #SMs), then normalises + affine (+SiLU) straight out of shared
+// memory.  The tensor is read from HBM/L2 once and written once.  Workspace layout per image b:
+// ws[b*(2G+2) + 0..2G) = {sum, sumsq} per group, then two int counters {arrived, done}; it must be
+// zero before the first launch and is left zero by the last CTA of each image.
+__device__ __forceinline__ int gn_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(512, 1)
+gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
+                const ea_half* __restrict__ x2, long long ldx2,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                ea_half* __restrict__ out, long long ldo, int HW, int C, int groups, float eps,
+                int silu, int chunks, int ppc, int cached, float* __restrict__ ws) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  float* sh = reinterpret_cast<float*>(gn_smem);                  // [2*groups]
+  uint4* cache = reinterpret_cast<uint4*>(gn_smem + 512);        // [ppc][nvec] (if cached)
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_cta;
-  const int p1 = min(HW, p0 + pix_per_cta);
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(HW, p0 + ppc);
+  const int nvec = C >> 3;
   const int cpg = C / groups;
+  const int lanes = blockDim.x / nvec;       // pixel lanes
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const bool active = pl < lanes;
+  const int c = v << 3;
+  float* wsb = ws + (long long)b * (2 * groups + 2);
+  int* cnt = reinterpret_cast<int*>(wsb + 2 * groups);
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  const int nvec = C >> 3;
-  // thread handles vector index v (fixed) for pixels p0 + k*(blockDim/nvec_rounded)...
-  // simple mapping: flat index over (pixel, vec)
-  const int total = (p1 - p0) * nvec;
-  // accumulate per-thread for up to two groups a vector may straddle; flush via smem atomics
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    int pp = idx / nvec;
-    int v = idx - pp * nvec;
-    int c = v << 3;
-    long long pix = (long long)b * HW + p0 + pp;
-    uint4 u;
-    if (c < C1) u = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + c));
-    else u = __ldg(reinterpret_cast<const uint4*>(x2 + pix * ldx2 + (c - C1)));
-    float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
-    float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-    int g0 = c / cpg;
-    int g7 = (c + 7) / cpg;
-    if (g0 == g7) {
-      float s = 0.f, q = 0.f;
+  // ---- pass 1: load (cache) + per-thread, per-channel partial sums (the thread's 8 channels
+  //      are fixed, so their groups are too: shared-memory atomics only once, after the loop)
+  float cs[8], cq[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s += vals[j]; q += vals[j] * vals[j]; }
-      atomicAdd(&sh[g0 * 2], s);
-      atomicAdd(&sh[g0 * 2 + 1], q);
-    } else {
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  const ea_half* src;
+  long long lds;
+  if (c < C1) { src = x + c; lds = ldx; } else { src = x2 + (c - C1); lds = ldx2; }
+  if (active) {
+    for (int pp = p0 + pl; pp < p1; pp += lanes) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pp) * lds));
+      if (cached) cache[(pp - p0) * nvec + v] = u;
+      float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
+      float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int g = (c + j) / cpg;
-        atomicAdd(&sh[g * 2], vals[j]);
-        atomicAdd(&sh[g * 2 + 1], vals[j] * vals[j]);
+      for (int j = 0; j < 8; ++j) { cs[j] += vals[j]; cq[j] += vals[j] * vals[j]; }
+    }
+    // combine channels of the same group before touching shared memory
+    int gprev = c / cpg;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      if (g != gprev) {
+        atomicAdd(&sh[gprev * 2], s);
+        atomicAdd(&sh[gprev * 2 + 1], q);
+        s = 0.f; q = 0.f; gprev = g;
       }
+      s += cs[j]; q += cq[j];
+    }
+    atomicAdd(&sh[gprev * 2], s);
+    atomicAdd(&sh[gprev * 2 + 1], q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&wsb[i], sh[i]);
+  __threadfence();
+  __syncthreads();
+  // ---- image-wide barrier
+  if (threadIdx.x == 0) {
+    atomicAdd(cnt, 1);
+    uint32_t spins = 0;
+    while (gn_ld_acquire(cnt) < chunks) {
+      __nanosleep(32);
+      if (++spins > (1u << 24)) { asm volatile("trap;"); }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&ws[(long long)b * groups * 2 + i], sh[i]);
-}
-
-// Pass 2: normalise + affine (+SiLU), 8 channels per thread.
-__global__ void gn_apply_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
-                                const ea_half* __restrict__ x2, long long ldx2,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                ea_half* __restrict__ out, long long ldo, int B, int HW, int C,
-                                int groups, float eps, int silu, const float* __restrict__ ws) {
-  const int nvec = C >> 3;
-  const long long total = (long long)B * HW * nvec;
-  const int cpg = C / groups;
-  const float inv_n = 1.0f / ((float)HW * (float)cpg);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long pix = idx / nvec;
-    int v = (int)(idx - pix * nvec);
-    int c = v << 3;
-    int b = (int)(pix / HW);
-    uint4 u;
-    if (c < C1) u = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + c));
-    else u = __ldg(reinterpret_cast<const uint4*>(x2 + pix * ldx2 + (c - C1)));
-    float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
-    float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-    float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-    float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-    float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-    int gprev = -1;
-    float mean = 0.f, rstd = 0.f;
+  __threadfence();
+  // ---- pass 2: y = x * a + b with a = rstd*gamma, b = beta - mean*a (per channel of this thread)
+  if (active) {
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    float av[8], bv[8];
+    {
+      float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+      int gprev = -1;
+      float mean = 0.f, rstd = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int g = (c + j) / cpg;
-      if (g != gprev) {
-        float s = ws[((long long)b * groups + g) * 2];
-        float q = ws[((long long)b * groups + g) * 2 + 1];
-        mean = s * inv_n;
-        float var = fmaxf(q * inv_n - mean * mean, 0.f);
-        rstd = rsqrtf(var + eps);
-        gprev = g;
+      for (int j = 0; j < 8; ++j) {
+        const int g = (c + j) / cpg;
+        if (g != gprev) {
+          const float s = __ldcg(&wsb[g * 2]), q = __ldcg(&wsb[g * 2 + 1]);
+          mean = s * inv_n;
+          rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
+          gprev = g;
+        }
+        av[j] = rstd * gm[j];
+        bv[j] = bt[j] - mean * av[j];
       }
-      float y = (vals[j] - mean) * rstd * gm[j] + bt[j];
-      vals[j] = silu ? silu_f(y) : y;
     }
-    uint4 o = make_uint4(ea_pack2(vals[0], vals[1]), ea_pack2(vals[2], vals[3]),
-                         ea_pack2(vals[4], vals[5]), ea_pack2(vals[6], vals[7]));
-    *reinterpret_cast<uint4*>(out + pix * ldo + c) = o;
+    for (int pp = p0 + pl; pp < p1; pp += lanes) {
+      uint4 u = cached ? cache[(pp - p0) * nvec + v]
+                       : __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pp) * lds));
+      float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
+      float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(vals[j], av[j], bv[j]);
+        vals[j] = silu ? silu_f(y) : y;
+      }
+      *reinterpret_cast<uint4*>(out + ((long long)b * HW + pp) * ldo + c) =
+          make_uint4(ea_pack2(vals[0], vals[1]), ea_pack2(vals[2], vals[3]),
+                     ea_pack2(vals[4], vals[5]), ea_pack2(vals[6], vals[7]));
+    }
+  }
+  // ---- leave the workspace zero for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int old = atomicAdd(cnt + 1, 1);
+    if (old == chunks - 1) {
+      for (int i = 0; i < groups * 2; ++i) wsb[i] = 0.f;
+      cnt[0] = 0;
+      cnt[1] = 0;
+    }
   }
 }
 
@@ -497,26 +535,43 @@ using namespace ea;
 
 extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
   if (!a || !a->x || !a->out || !a->gamma || !a->beta || !a->workspace) return EA_ERR_ARG;
-  if (a->C % 8 != 0 || a->C % a->groups != 0 || a->ldx % 8 != 0 || a->ldo % 8 != 0)
+  if (a->C % 8 != 0 || a->C % a->groups != 0 || a->ldx % 8 != 0 || a->ldo % 8 != 0 ||
+      a->groups > 64 || a->C / 8 > 512)
     return EA_ERR_SHAPE;
   const int C1 = a->x2 ? a->C1 : a->C;
   if (a->x2 && (C1 % 8 != 0 || a->ldx2 % 8 != 0)) return EA_ERR_SHAPE;
   cudaStream_t st = EA_STREAM(stream);
-  if (cudaMemsetAsync(a->workspace, 0, sizeof(float) * 2 * a->B * a->groups, st) != cudaSuccess)
-    return EA_ERR_CUDA;
-  int chunks = a->HW >= 64 ? 64 : a->HW;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
+      n_sm = 148;
+  }
+  if (a->B > n_sm) return EA_ERR_SHAPE;
+  int chunks = n_sm / a->B;                 // all CTAs resident (they barrier on each other)
+  if (chunks > a->HW) chunks = a->HW;
   int ppc = (a->HW + chunks - 1) / chunks;
   chunks = (a->HW + ppc - 1) / ppc;
-  dim3 g1(chunks, a->B);
-  gn_stats_kernel<<<g1, 256, a->groups * 2 * sizeof(float), st>>>(
+  const int nvec = a->C / 8;
+  int threads = (512 / nvec) * nvec;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  const long long cache_bytes = (long long)ppc * nvec * 16;
+  const int cached = cache_bytes <= 200 * 1024;
+  const int smem = 512 + (cached ? (int)cache_bytes : 0);
+  static int max_set = 0;
+  if (smem > max_set) {
+    if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return EA_ERR_CUDA;
+    max_set = smem;
+  }
+  dim3 grid(chunks, a->B);
+  gn_fused_kernel<<<grid, threads, smem, st>>>(
       reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
-      a->ldx2, a->HW, a->C, a->groups, ppc, a->workspace);
-  ea_count_launch();
-  long long total = (long long)a->B * a->HW * (a->C / 8);
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-      reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
-      a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->B, a->HW, a->C,
-      a->groups, a->eps, a->silu, a->workspace);
+      a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
+      a->groups, a->eps, a->silu, chunks, ppc, cached, a->workspace);
   return EA_LAUNCH_OK();
 }
 

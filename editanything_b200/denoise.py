@@ -86,7 +86,7 @@ class DenoiseEngine:
         if not hasattr(self, "t_dev") or self.t_dev.shape[0] != self.B:
             self.t_dev = torch.zeros(self.B, device=self.dev, dtype=torch.float32)
             self.coef_dev = torch.zeros(4, device=self.dev, dtype=torch.float32)
-            self.gn_ws = torch.empty(self.B * 32 * 2, device=self.dev, dtype=torch.float32)
+            self.gn_ws = torch.zeros(self.B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
             self._graph = None
 
     # -- parity API: the network output itself ------------------------------------------------

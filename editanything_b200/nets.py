@@ -359,7 +359,7 @@ class UNetRunner:
         o = self.ops
         B, H, W_, _ = x_half.shape
         if gn_ws is None:
-            gn_ws = torch.empty(B * 32 * 2, device=self.dev, dtype=torch.float32)
+            gn_ws = torch.zeros(B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
         sinks = self.alloc_sinks(B, H, W_)
         emb_u = un._emb(t_dev, B)
         self._encoder(un, x_half, emb_u, ctx_cache[0], gn_ws, sinks=sinks)

@@ -32,10 +32,25 @@ def reset_launch_count():
     L.load().ea_reset_launch_count()
 
 
+_GEMM_WS = {}
+GEMM_WS_BYTES = 65536 + 48 * 1024 * 1024
+
+
+def gemm_workspace(device):
+    """Per-device split-K scratch of ea_gemm (64 KB zeroed counters + fp32 partial tiles); shared by
+    every GEMM on the stream, allocated once so CUDA-graph captures see a stable address."""
+    key = (device.type, device.index)
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(GEMM_WS_BYTES, device=device, dtype=torch.uint8)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
          conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
          out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
-         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0):
+         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0):
     """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes."""
     lib = L.lib()
     g = L.GemmArgs()
@@ -83,6 +98,10 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     g.accumulate = 1 if accumulate else 0
     g.force_bn = force_bn
     g.force_stages = force_stages
+    g.force_splits = force_splits
+    ws = gemm_workspace(a.device)
+    g.workspace = ws.data_ptr()
+    g.workspace_bytes = ws.numel()
     L.check(lib.ea_gemm(C.byref(g), _stream()), "ea_gemm")
     return out if out is not None else out_f32
 
@@ -121,7 +140,7 @@ def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True,
     g.B, g.HW, g.C, g.groups = B, HW, C_, groups
     g.eps, g.silu = eps, 1 if silu else 0
     if workspace is None:
-        workspace = torch.empty(B * groups * 2, device=x.device, dtype=torch.float32)
+        workspace = torch.zeros(B * (groups * 2 + 2), device=x.device, dtype=torch.float32)
     g.workspace = workspace.data_ptr()
     L.check(lib.ea_groupnorm(C.byref(g), _stream()), "ea_groupnorm")
     return out

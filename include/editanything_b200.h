@@ -66,6 +66,10 @@ void ea_reset_launch_count(void);
  *                 -> (+= out[m,n] if accumulate) -> store out (and out2).
  * act GEGLU: W rows must be pre-interleaved per 128-row block as [64 value rows | 64 gate rows];
  *            output has N/2 columns: value * gelu(gate)   (attention.py:54-56).
+ * Split-K: when the output has fewer tiles than the GPU has SMs, K is split across CTAs; each
+ *            split CTA publishes its fp32 partial tile to `workspace`, waits for its siblings
+ *            (all resident by construction) and finishes a 1/splits share of the tile with the
+ *            full fused epilogue — deterministic summation order, no extra launch.
  * Constraints: N % 8 == 0, K % 8 == 0, Cin % 64 == 0, all leading dims % 8 == 0,
  *              pointers 16-byte aligned.
  */
@@ -96,6 +100,11 @@ typedef struct ea_gemm_args {
   int accumulate;
   int force_bn;              /* 0 = auto; else 32/64/128/256 (testing) */
   int force_stages;          /* 0 = auto */
+  int force_splits;          /* 0 = auto; 1 = never split K; n = split K n ways (testing) */
+  void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
+  long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
+                                (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K
+                                is never split.  One workspace may serve every call on a stream. */
 } ea_gemm_args;
 int ea_gemm(const ea_gemm_args* args, void* stream);
 
@@ -131,7 +140,8 @@ typedef struct ea_gn_args {
   void* out; long long ldo;
   int B, HW, C, groups;
   float eps; int silu;
-  float* workspace;          /* >= B*groups*2 floats */
+  float* workspace;          /* >= B*(2*groups+2) floats, ZERO before the first call (the kernel
+                                leaves it zero); one workspace may serve every call on a stream */
 } ea_gn_args;
 int ea_groupnorm(const ea_gn_args* args, void* stream);
 int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, void* out,

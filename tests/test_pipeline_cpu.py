@@ -1,0 +1,161 @@
+"""`StableDiffusionControlNetInpaintPipeline` host logic (call surface, check_inputs errors, latent /
+mask / conditioning preparation, loop + blend semantics) against a straight re-enactment of the
+reference loop (utils/stable_diffusion_controlnet_inpaint.py:1540-1664) on the CPU oracle.  The
+engine's operators are emulated on CPU (tests/cpu_ops.py)."""
+import math
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from editanything_b200.denoise import DenoiseEngine
+from editanything_b200.pipeline import (DDIMScheduler, StableDiffusionControlNetInpaintPipeline,
+                                        prepare_controlnet_conditioning_image, prepare_mask_image)
+from editanything_b200.unet_spec import TINY, build_topology, make_state_dict
+from oracle import unet_oracle as O
+from tests import cpu_ops
+
+
+class FakeVAE:
+    """Deterministic stand-in with the diffusers AutoencoderKL surface the pipeline touches."""
+    config = SimpleNamespace(scaling_factor=0.18215, latent_channels=4, block_out_channels=(1, 2, 3, 4))
+
+    def encode(self, x):
+        z = F.avg_pool2d(x, 8)
+        z = torch.cat([z, z.mean(1, keepdim=True)], 1)
+        return SimpleNamespace(latent_dist=SimpleNamespace(sample=lambda generator=None: z))
+
+    def decode(self, z):
+        return SimpleNamespace(sample=F.interpolate(z[:, :3], scale_factor=8, mode="nearest"))
+
+
+def _setup(n_cn=2):
+    cfg = TINY
+    usd = make_state_dict(cfg, "unet", 51)
+    csds = [make_state_dict(cfg, "controlnet", 52 + i) for i in range(n_cn)]
+    eng = DenoiseEngine(cfg, usd, csds, torch.device("cpu"), backend=cpu_ops)
+    pipe = StableDiffusionControlNetInpaintPipeline(eng, vae=FakeVAE())
+    g = torch.Generator().manual_seed(0)
+    H = W = 64
+    image = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+    mask = torch.zeros(1, 1, H, W)
+    mask[:, :, 16:48, 8:40] = 1.0
+    conds = [torch.randint(0, 256, (1, 3, H, W), generator=g).float(), torch.rand(1, 3, H, W, generator=g)][:n_cn]
+    pe = torch.randn(1, 9, cfg.context_dim, generator=g)
+    ne = torch.randn(1, 9, cfg.context_dim, generator=g)
+    return cfg, usd, csds, pipe, image, mask, conds, pe, ne
+
+
+def _reference_loop(cfg, usd, csds, image, mask, conds, pe, ne, steps, gs, scales, seed, alignment_ratio, n_img=1):
+    """The reference __call__ re-enacted with the oracle networks (in_channels == 4 branch)."""
+    vae = FakeVAE()
+    sch = DDIMScheduler()
+    sch.set_timesteps(steps)
+    ts = sch.timesteps
+    ctx = torch.cat([ne.repeat(n_img, 1, 1), pe.repeat(n_img, 1, 1)])
+    hints = [torch.cat([c.repeat_interleave(n_img, 0)] * 2) for c in conds]
+    lat = torch.randn((n_img, 4, 8, 8), generator=torch.Generator().manual_seed(seed))
+    noise = lat
+    init = 0.18215 * vae.encode(image).latent_dist.sample().repeat(n_img, 1, 1, 1)
+    m = 1 - F.interpolate((mask >= 0.5).float(), (8, 8), mode="nearest")
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    for i, t in enumerate(ts):
+        x_in = torch.cat([lat] * 2)
+        with torch.no_grad():
+            e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], x_in, torch.full((2 * n_img,), int(t)), ctx, hints,
+                              scales)
+        e = e[:n_img] + gs * (e[n_img:] - e[:n_img])
+        lat = sch.step(e, t, lat).prev_sample
+        if alignment_ratio is not None and i < len(ts) * alignment_ratio:
+            lat = sch.add_noise(init, noise, ts[i + 1]) * m + lat * (1 - m)
+    if alignment_ratio is None or alignment_ratio == 1.0:
+        lat = init * m + lat * (1 - m)
+    return lat
+
+
+@pytest.mark.parametrize("alignment_ratio", [None, 0.5])
+def test_call_matches_reference_loop(alignment_ratio):
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup()
+    out = pipe(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+               num_inference_steps=4, guidance_scale=9.0, generator=torch.manual_seed(7), prompt_embeds=pe,
+               negative_prompt_embeds=ne, output_type="latent", controlnet_conditioning_scale=[0.5, 1.0],
+               alignment_ratio=alignment_ratio, num_images_per_prompt=1)
+    ref = _reference_loop(cfg, usd, csds, image, mask, conds, pe, ne, 4, 9.0, [0.5, 1.0], 7, alignment_ratio)
+    assert out.images.shape == (1, 4, 8, 8)
+    assert (out.images - ref).abs().max().item() < 2e-4
+
+
+def test_generic_scheduler_path_and_decode():
+    """A scheduler that is not the built-in DDIM (the demos install UniPC) goes through
+    engine.eps + scheduler.step; output_type='np' decodes through the attached VAE."""
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup(n_cn=1)
+
+    class OtherDDIM:                      # same math, different class -> generic path
+        def __init__(self):
+            self._s = DDIMScheduler()
+            self.order, self.init_noise_sigma = 1, 1.0
+
+        def set_timesteps(self, n, device=None):
+            self._s.set_timesteps(n)
+            self.timesteps = self._s.timesteps
+
+        def scale_model_input(self, x, t):
+            return x
+
+        def step(self, e, t, x, **kw):
+            return self._s.step(e, t, x)
+
+        def add_noise(self, a, b, t):
+            return self._s.add_noise(a, b, t)
+
+    kw = dict(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+              num_inference_steps=4, guidance_scale=5.0, prompt_embeds=pe, negative_prompt_embeds=ne,
+              controlnet_conditioning_scale=[0.8], alignment_ratio=None)
+    a = pipe(generator=torch.manual_seed(3), output_type="latent", **kw).images
+    pipe.scheduler = OtherDDIM()
+    b = pipe(generator=torch.manual_seed(3), output_type="latent", **kw).images
+    assert (a - b).abs().max().item() < 1e-4
+    imgs = pipe(generator=torch.manual_seed(3), output_type="np", return_dict=False, **kw)[0]
+    assert imgs.shape == (1, 64, 64, 3) and imgs.min() >= 0 and imgs.max() <= 1
+
+
+def test_check_inputs_errors_match_reference_types():
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup()
+    ok = dict(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+              prompt_embeds=pe, negative_prompt_embeds=ne, controlnet_conditioning_scale=[0.5, 1.0],
+              num_inference_steps=1, output_type="latent")
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "height": 60})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "callback_steps": 0})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "prompt": "a cat"})                           # both prompt and prompt_embeds
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "prompt_embeds": None})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "negative_prompt_embeds": ne[:, :5]})
+    with pytest.raises(TypeError):
+        pipe(**{**ok, "controlnet_conditioning_image": conds[0]})   # multi-controlnet needs a list
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "controlnet_conditioning_image": conds[:1]})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "controlnet_conditioning_scale": [1.0]})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "image": image * 3})
+    with pytest.raises(ValueError):
+        pipe(**{**ok, "mask_image": mask[:, :, :32]})
+    with pytest.raises(IndexError):
+        pipe(**{**ok, "alignment_ratio": 1.0})                      # reference quirk: timesteps[i + 1]
+    with pytest.raises(NotImplementedError):
+        pipe(**{**ok, "ref_image": image})
+
+
+def test_preparation_helpers():
+    m = prepare_mask_image(torch.tensor([[0.2, 0.7], [0.5, 0.49]]))
+    assert m.shape == (1, 1, 2, 2) and m.flatten().tolist() == [0.0, 1.0, 1.0, 0.0]
+    c = prepare_controlnet_conditioning_image(torch.full((1, 3, 8, 8), 200.0), 8, 8, 3, 3, torch.float32, True)
+    assert c.shape == (6, 3, 8, 8) and float(c.max()) == 200.0     # un-normalised, repeated, CFG-doubled
+    s = DDIMScheduler()
+    s.set_timesteps(30)
+    assert len(s.timesteps) == 31 and int(s.timesteps[0]) == 991    # reference quirk: S=30 -> 31 steps

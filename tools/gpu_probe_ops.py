@@ -72,6 +72,55 @@ def case_gemm_ktail():
     return case_gemm_linear(M=154, N=320, K=776)  # K not a multiple of 64, M ragged
 
 
+def case_gemm_splitk():
+    """Small-M, long-K problems: the planner splits K; also forced split counts (3, 7) and a
+    repeat launch (the in-kernel counters must have been re-armed)."""
+    import torch
+    from editanything_b200 import ops
+    dt = ops.half_dtype()
+    torch.manual_seed(11)
+    res, worst = {}, 0.0
+    for (M, N, K, fs) in [(128, 1280, 11520, 0), (128, 1280, 5120, 3), (512, 1280, 2560, 0), (100, 320, 1288, 7),
+                          (128, 1280, 11520, 0)]:
+        a = torch.randn(M, K, device="cuda").to(dt)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dt)
+        bias = torch.randn(N, device="cuda")
+        resid = torch.randn(M, N, device="cuda").to(dt)
+        out = torch.full((M, N), 7.0, device="cuda", dtype=dt)
+        ops.gemm(a, w, out, bias=bias, residual=resid, force_splits=fs)
+        torch.cuda.synchronize()
+        e = _err(out, a.float() @ w.float().t() + bias + resid.float())
+        res[f"{M}x{N}x{K}/s{fs}#{len(res)}"] = e
+        worst = max(worst, e["max_abs"] / max(1.0, e["ref_max"]))
+    ws = ops.gemm_workspace(torch.device("cuda", torch.cuda.current_device()))
+    res["counters_rearmed"] = int(ws[:65536].view(torch.int32).abs().sum().item())
+    res["max_abs"] = worst if res["counters_rearmed"] == 0 else 1e9
+    res["ref_max"] = 1.0
+    return res
+
+
+def case_gemm_splitk_geglu():
+    import torch
+    from editanything_b200 import ops, _lib as L
+    dt = ops.half_dtype()
+    torch.manual_seed(12)
+    M, C_, F = 128, 1280, 1280  # proj: C -> 2F, small M => planner may split K; also forced
+    a = torch.randn(M, C_, device="cuda").to(dt)
+    w = (torch.randn(2 * F, C_, device="cuda") / C_ ** 0.5).to(dt)
+    b = torch.randn(2 * F, device="cuda")
+    idx = torch.cat([torch.cat([torch.arange(j * 64, j * 64 + 64), F + torch.arange(j * 64, j * 64 + 64)])
+                     for j in range(F // 64)]).cuda()
+    y = a.float() @ w.float().t() + b
+    ref = y[:, :F] * torch.nn.functional.gelu(y[:, F:])
+    worst = 0.0
+    for fs in (0, 4):
+        out = ops.gemm(a, w[idx].contiguous(), bias=b[idx].contiguous(), act=L.EA_ACT_GEGLU, force_splits=fs)
+        torch.cuda.synchronize()
+        e = _err(out, ref)
+        worst = max(worst, e["max_abs"] / max(1.0, e["ref_max"]))
+    return {"max_abs": worst, "ref_max": 1.0}
+
+
 def case_gemm_geglu():
     import torch
     from editanything_b200 import ops, _lib as L
@@ -159,6 +208,10 @@ def case_conv_32():
 
 def case_conv_8():
     return _conv_case(2, 8, 8, 1280, 1280)
+
+
+def case_conv_8_skip_splitk():
+    return _conv_case(2, 8, 8, 1280, 1280, extra=2560)
 
 
 def case_conv_8_b1():
