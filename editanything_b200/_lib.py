@@ -65,11 +65,14 @@ SYMBOLS = {
     "ea_init": (_I, []),
     "ea_launch_count": (_L, []),
     "ea_reset_launch_count": (None, []),
+    "ea_set_pdl": (None, [_I]),
     "ea_gemm": (_I, [C.POINTER(GemmArgs), _P]),
+    "ea_gemm_plan": (_I, [_I, _I, _I, _I, _L, _I, C.POINTER(C.c_int)]),
     "ea_attention": (_I, [C.POINTER(AttnArgs), _P]),
     "ea_groupnorm": (_I, [C.POINTER(GnArgs), _P]),
     "ea_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
     "ea_conv_direct": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "ea_conv_in": (_I, [_P, _P, _P, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
     "ea_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ea_small_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),

@@ -22,6 +22,8 @@ def _stale():
 
 def build(force=False, verbose=False, extra=()):
     """Compile every .cu for sm_100a into editanything_b200/lib/libea_b200.so."""
+    if os.environ.get("EA_NVCC_EXTRA"):
+        force = True
     if not force and not _stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -32,7 +34,7 @@ def build(force=False, verbose=False, extra=()):
         obj = os.path.join(PKG, "lib", src.replace(".cu", ".o"))
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DEA_PRECISE_MATH",
-               "-c", os.path.join(HERE, src), "-o", obj] + list(extra)
+               "-c", os.path.join(HERE, src), "-o", obj] + list(extra) + os.environ.get("EA_NVCC_EXTRA", "").split()
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -1,5 +1,6 @@
 // ea_api.cu — library bookkeeping for the C ABI declared in include/editanything_b200.h.
 #include <atomic>
+#include <stdlib.h>
 #include "ea_common.cuh"
 #include "ea_internal.h"
 
@@ -26,6 +27,16 @@ ea_tmap_encode_fn ea_tmap_encode() {
   }
   return g_encode;
 }
+
+static int g_pdl = -1;
+int ea_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("EA_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+extern "C" void ea_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 void ea_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

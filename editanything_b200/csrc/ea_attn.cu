@@ -38,6 +38,7 @@ struct AttnKParams {
   int dpad16;  // d rounded up to 16: MMA N of the PV product
   int stages;
   int p_smem;  // 1: stage P through shared memory (SS MMA) instead of TMEM (testing fallback)
+  int dbg_skip;  // experiment builds: bit0 = skip the PV MMAs, bit1 = skip the S MMAs, bit2 = V K-major view
   float scale_log2;
   ea_half* out;
   long long o_bs, o_ns;
@@ -45,6 +46,19 @@ struct AttnKParams {
   const float* rel_w;
   int rel_s;
 };
+
+#ifdef EA_ATTN_TIMING
+// Experiment build only (-DEA_ATTN_TIMING): per-phase clock64 stamps of CTA (0,0,0), softmax warps
+// 4 and 8 (lane 0), KV tiles 8..15; read back with ea_attn_debug_read().
+__device__ long long ea_attn_dbg[2 * 8 * 8];
+__device__ long long ea_attn_dbg_mma[2 * 8 * 4];   // per (tile, kv 8..15): p_ready seen, PV issued, S issued
+#define EA_T(slot)                                                                          \
+  do {                                                                                      \
+    if (dbg_on && j >= 8 && j < 16) ea_attn_dbg[(t * 8 + (j - 8)) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define EA_T(slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -57,7 +71,7 @@ __device__ __forceinline__ void tmem_st16_half(uint32_t taddr, const uint32_t (&
 }
 
 template <int NQT, bool BIAS>
-__global__ void __launch_bounds__(128 + 128 * NQT, 1)
+__global__ void __launch_bounds__(128 * NQT + 64, 1)
 ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -77,12 +91,17 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* pv_done = p_ready + 2;              // [2]  per tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Nkv + AT_BKV - 1) / AT_BKV;
 
-  if (warp == 0 && lane == 0) {
+  // Warp roles: softmax warpgroups FIRST (warps 0..4*NQT-1; warp % 4 = TMEM lane quarter), then the
+  // TMA and MMA warps.  The SM's warp arbiter prefers the highest warp id among eligible warps, and
+  // the single MMA-issuing thread must never queue behind the eight busy softmax warps.
+  constexpr int W_TMA = 4 * NQT, W_MMA = 4 * NQT + 1;
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -98,13 +117,14 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       mbar_expect_tx(q_full, (uint32_t)(NQT * p.nd * AT_ATOM));
@@ -126,37 +146,57 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ============================= MMA issuer =============================
     if (lane == 0) {
+      // Issue loops are kept to a few scalar instructions per MMA (descriptor = base + small add):
+      // a single thread retires about one dependent instruction per 4-5 cycles, and at d = 40 an
+      // MMA itself only takes 24-64 cycles (measured: tools/exp/mma_rate2.cu).
       const uint32_t idesc_s = umma_idesc(128, 128, 0, 0);
       const uint32_t idesc_o = umma_idesc(128, (uint32_t)p.dpad16, 0, 1);  // B (=V) MN-major
-      const uint32_t aQ = smem_u32(sQ);
-      const uint32_t aKV = smem_u32(sKV);
-      const uint32_t aP = smem_u32(sP);
-      // S_t(j) = Q_t K_j^T into TMEM columns s_col
+      const uint64_t dQ0 = umma_desc_k_sw128(smem_u32(sQ), 1024);
+      const uint64_t dK0 = umma_desc_k_sw128(smem_u32(sKV), 1024);
+      const uint64_t dV0 = umma_desc_mn_sw128(smem_u32(sKV) + (uint32_t)(p.nd * AT_ATOM), AT_ATOM, 1024);
+      const uint64_t dP0 = umma_desc_k_sw128(smem_u32(sP), 1024);
+      const uint32_t q_tile16 = (uint32_t)(p.nd * AT_ATOM) >> 4;
+      const uint32_t kv_stage16 = (uint32_t)kv_stage_bytes >> 4;
+      const int ksteps = p.ksteps;
+      const bool p_smem = p.p_smem != 0;
+      // S_t(j) = Q_t K_j^T into TMEM columns s_col.  K-step ks sits at atom (ks >> 2), +32 B * (ks & 3)
       auto issue_S = [&](int t, int stage, uint32_t s_col) {
-        const uint32_t q0 = aQ + (uint32_t)(t * p.nd * AT_ATOM);
-        const uint32_t k0 = aKV + (uint32_t)(stage * kv_stage_bytes);
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * AT_ATOM + (ks & 3) * 32);
-          umma_f16_ss(tmem_base + s_col, umma_desc_k_sw128(q0 + off, 1024),
-                      umma_desc_k_sw128(k0 + off, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        uint64_t dq = dQ0 + (uint64_t)(t * q_tile16);
+        uint64_t dk = dK0 + (uint64_t)(stage * kv_stage16);
+        const uint32_t d = tmem_base + s_col;
+        umma_f16_ss(d, dq, dk, idesc_s, 0u);
+        for (int ks = 1; ks < ksteps; ++ks) {
+          const uint32_t step = (ks & 3) ? 2u : (uint32_t)((AT_ATOM >> 4) - 6);
+          dq += step;
+          dk += step;
+          umma_f16_ss(d, dq, dk, idesc_s, 1u);
         }
       };
       // O_t += P_t(j) V_j ; P lives in TMEM columns p_col (16-bit pairs) or in smem tile t
       auto issue_PV = [&](int t, int stage, uint32_t p_col, uint32_t o_col, bool first) {
-        const uint32_t v0 = aKV + (uint32_t)(stage * kv_stage_bytes + p.nd * AT_ATOM);
-        for (int ks = 0; ks < AT_BKV / 16; ++ks) {
-          const uint64_t dV = umma_desc_mn_sw128(v0 + (uint32_t)(ks * 16 * 128), AT_ATOM, 1024);
-          const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
-          if (p.p_smem) {
-            const uint32_t offP =
-                (uint32_t)(t * 2 * AT_ATOM + (ks >> 2) * AT_ATOM + (ks & 3) * 32);
-            umma_f16_ss(tmem_base + o_col, umma_desc_k_sw128(aP + offP, 1024), dV, idesc_o, acc);
-          } else {
-            umma_f16_ts(tmem_base + o_col, tmem_base + p_col + (uint32_t)(ks * 8), dV, idesc_o,
-                        acc);
+        uint64_t dv = dV0 + (uint64_t)(stage * kv_stage16);
+        const uint32_t d = tmem_base + o_col;
+        uint32_t acc = first ? 0u : 1u;
+        if (p_smem) {
+          uint64_t dp = dP0 + (uint64_t)(t * (2 * AT_ATOM >> 4));
+#pragma unroll
+          for (int ks = 0; ks < AT_BKV / 16; ++ks) {
+            umma_f16_ss(d, dp, dv, idesc_o, acc);
+            acc = 1u;
+            dp += (ks & 3) == 3 ? (uint64_t)((AT_ATOM >> 4) - 6) : 2u;
+            dv += (16 * 128) >> 4;
+          }
+        } else {
+          uint32_t pa = tmem_base + p_col;
+#pragma unroll
+          for (int ks = 0; ks < AT_BKV / 16; ++ks) {
+            umma_f16_ts(d, pa, dv, idesc_o, acc);
+            acc = 1u;
+            pa += 8u;
+            dv += (16 * 128) >> 4;
           }
         }
       };
@@ -179,9 +219,16 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int t = 0; t < 2; ++t) {
             mbar_wait(&p_ready[t], (uint32_t)(j & 1));
             tc_fence_after();
+#ifdef EA_ATTN_TIMING
+            const bool md = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 8 && j < 16;
+            if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 0] = clock64();
+#endif
             issue_PV(t, stage, (uint32_t)(t * 128), (uint32_t)(256 + t * 128), j == 0);
             umma_commit(&pv_done[t]);
             if (t == 1) umma_commit(&kv_empty[stage]);
+#ifdef EA_ATTN_TIMING
+            if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 1] = clock64();
+#endif
             if (more) {
               if (t == 0) {
                 mbar_wait(&kv_full[nstage], nphase);
@@ -190,6 +237,9 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               issue_S(t, nstage, (uint32_t)(t * 128));
               umma_commit(&s_full[t]);
             }
+#ifdef EA_ATTN_TIMING
+            if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 2] = clock64();
+#endif
           }
           stage = nstage;
           phase = nphase;
@@ -229,9 +279,9 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ======================= softmax / correction / epilogue ==============
-    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int t = warp >> 2;        // query tile of this warpgroup
     const int wq = warp & 3;        // TMEM lane quarter accessible to this warp
     const int r = wq * 32 + lane;
     const int q = (qb * NQT + t) * AT_BQ + r;
@@ -248,11 +298,16 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     float m_run = -INFINITY;  // running max in the scaled log2 domain
     float l = 0.f;
+#ifdef EA_ATTN_TIMING
+    const bool dbg_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = (NQT == 2) ? t : (j & 1);
       const uint32_t sph = (NQT == 2) ? (uint32_t)(j & 1) : (uint32_t)((j >> 1) & 1);
+      EA_T(0);
       mbar_wait(&s_full[sb], sph);
       tc_fence_after();
+      EA_T(1);
       const uint32_t tmem_S = tmem_base + lane_off + (uint32_t)sb * 128u;
       const int valid = min(AT_BKV, p.Nkv - j * AT_BKV);  // keys of this tile that exist (>= 1)
       if (!BIAS) {
@@ -263,6 +318,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld32(tmem_S + 64u, v[2]);
         tmem_ld32(tmem_S + 96u, v[3]);
         tmem_ld_wait();
+        EA_T(2);
         if (valid < AT_BKV) {  // last, partial K/V tile: keys that do not exist get -inf
 #pragma unroll
           for (int h = 0; h < 4; ++h)
@@ -301,6 +357,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_st_wait();
         }
         const float neg_m = -m_run;
+        EA_T(3);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -414,10 +471,12 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       }  // BIAS
+      EA_T(4);
       if (p.p_smem) fence_proxy_async();
       else tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[t]);
+      EA_T(5);
     }
     // ---- epilogue: O / l
     mbar_wait(&pv_done[t], (uint32_t)((n_tiles - 1) & 1));
@@ -449,7 +508,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -478,13 +537,24 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
       return EA_ERR_CUDA;
     max_set = smem_bytes;
   }
-  ea_attn_kernel<NQT, BIAS><<<grid, 128 + 128 * NQT, smem_bytes, stream>>>(tq, tk, tv, p);
-  return 0;
+  return ea_launch(ea_attn_kernel<NQT, BIAS>, grid, dim3(128 * NQT + 64), (size_t)smem_bytes, stream,
+                   tq, tk, tv, p) == cudaSuccess ? 0 : EA_ERR_CUDA;
 }
 
 }  // namespace ea
 
 using namespace ea;
+
+#ifdef EA_ATTN_TIMING
+extern "C" int ea_attn_debug_read(long long* host_out, int n) {
+  if (n > 2 * 8 * 8) n = 2 * 8 * 8;
+  return cudaMemcpyFromSymbol(host_out, ea_attn_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : EA_ERR_CUDA;
+}
+extern "C" int ea_attn_debug_read_mma(long long* host_out, int n) {
+  if (n > 2 * 8 * 4) n = 2 * 8 * 4;
+  return cudaMemcpyFromSymbol(host_out, ea_attn_dbg_mma, sizeof(long long) * n) == cudaSuccess ? 0 : EA_ERR_CUDA;
+}
+#endif
 
 extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -507,6 +577,8 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   p.ksteps = (a->d + 15) / 16;
   p.dpad16 = p.ksteps * 16;
   p.p_smem = force_p_smem;
+  static const int dbg_skip = [] { const char* e = getenv("EA_ATTN_SKIP"); return e ? atoi(e) : 0; }();
+  p.dbg_skip = dbg_skip;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<ea_half*>(a->out);
   p.o_bs = a->o_bs; p.o_ns = a->o_ns;

@@ -263,6 +263,15 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N, 
   return d;
 }
 
+// ------------------------- programmatic dependent launch -------------------
+// wait: all prerequisite grids have completed and their writes are visible (no-op when the kernel
+// was not launched with the programmatic-serialisation attribute).  launch_dependents: the next
+// kernel on the stream may start its prologue once every CTA of this grid has issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // --------------------------------- math ------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {

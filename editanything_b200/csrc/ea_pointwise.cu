@@ -27,6 +27,8 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 ea_half* __restrict__ out, long long ldo, int HW, int C, int groups, float eps,
                 int silu, int chunks, int ppc, int cached, float* __restrict__ ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   float* sh = reinterpret_cast<float*>(gn_smem);                  // [2*groups]
   uint4* cache = reinterpret_cast<uint4*>(gn_smem + 512);        // [ppc][nvec] (if cached)
@@ -151,6 +153,8 @@ __global__ void layernorm_kernel(const ea_half* __restrict__ x, long long ldx,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  ea_half* __restrict__ out, long long ldo, int M, int C,
                                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
@@ -216,6 +220,8 @@ __global__ void conv_direct_kernel(const ea_half* __restrict__ x, const float* _
                                    const float* __restrict__ bias, ea_half* __restrict__ out,
                                    int B, int Hin, int Win, int Cin, int Cout, int ks, int stride,
                                    int silu, const ea_half* __restrict__ add, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
   const long long total = (long long)B * Ho * Wo * Cout;
   const int pad = ks / 2;
@@ -246,6 +252,8 @@ __global__ void conv_direct_kernel(const ea_half* __restrict__ x, const float* _
 
 __global__ void upsample2x_kernel(const ea_half* __restrict__ x, ea_half* __restrict__ out, int B,
                                   int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = C >> 3;
   const long long total = (long long)B * (2 * H) * (2 * W) * nvec;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -265,6 +273,8 @@ __global__ void upsample2x_kernel(const ea_half* __restrict__ x, ea_half* __rest
 __global__ void small_linear_kernel(const float* __restrict__ x, const ea_half* __restrict__ w,
                                     const float* __restrict__ bias, float* __restrict__ y, int M,
                                     int N, int K, int silu_in, int silu_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -305,6 +315,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const ea_half* 
 // util.py:154-174: freqs = exp(-ln(10000) * i / half), emb = [cos(t f) | sin(t f)]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out,
                                           int B, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
@@ -324,6 +336,8 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
                                     float guidance, const float* __restrict__ known,
                                     const float* __restrict__ mask, ea_half* __restrict__ lat_half,
                                     int Nimg, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long npix = (long long)Nimg * H * W;
@@ -402,6 +416,8 @@ __global__ void sam_relpos_kernel(const ea_half* __restrict__ q, long long q_bs,
                                   const float* __restrict__ Rh, const float* __restrict__ Rw,
                                   float* __restrict__ rel_h, float* __restrict__ rel_w, int B,
                                   int heads, int S, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * heads * S * S * 2 * S;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -428,6 +444,8 @@ __global__ void sam_relpos_kernel(const ea_half* __restrict__ q, long long q_bs,
 
 __global__ void window_partition_kernel(const ea_half* __restrict__ x, ea_half* __restrict__ out,
                                         int B, int H, int W, int C, int ws, int nWh, int nWw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = C >> 3;
   const long long total = (long long)B * nWh * nWw * ws * ws * nvec;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -451,6 +469,8 @@ __global__ void window_unpartition_kernel(const ea_half* __restrict__ xw,
                                           const ea_half* __restrict__ residual,
                                           ea_half* __restrict__ out, int B, int H, int W, int C,
                                           int ws, int nWh, int nWw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = C >> 3;
   const long long total = (long long)B * H * W * nvec;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -480,6 +500,8 @@ __global__ void window_unpartition_kernel(const ea_half* __restrict__ xw,
 // order, so the convolution is one ea_gemm.  Thread <-> 8 consecutive kw.
 __global__ void patchify_kernel(const float* __restrict__ img, ea_half* __restrict__ out, int B,
                                 int Cin, int H, int W, int ps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gh = H / ps, gw = W / ps;
   const int K = Cin * ps * ps;
   const int kvec = K >> 3;
@@ -507,6 +529,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, ea_half* __restri
 // NHWC half -> NCHW fp32 (the layout/precision the reference hands to the prompt/mask decoder).
 __global__ void nhwc_to_nchw_f32_kernel(const ea_half* __restrict__ x, float* __restrict__ out,
                                         int B, int HW, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -518,6 +542,65 @@ __global__ void nhwc_to_nchw_f32_kernel(const ea_half* __restrict__ x, float* __
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int c = c0 + i, p = p0 + threadIdx.x;
     if (p < HW && c < C) out[((long long)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// 3x3 stride-1 pad-1 convolution with a tiny input depth (conv_in: 4 -> 320, openaimodel.py:533-539,
+// and ControlNet `h = conv_in(x) + guided_hint`, cldm/cldm.py:293-297).  K = 9*Cin is far too small for
+// the tensor-core path; the whole filter bank lives in shared memory, a thread owns one pixel and 8
+// consecutive output channels (16-byte stores), the 9*Cin input taps sit in registers.
+template <int CIN>
+__global__ void conv_smallcin_kernel(const ea_half* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ bias, ea_half* __restrict__ out,
+                                     long long ldo, ea_half* __restrict__ out2, long long ldo2,
+                                     const ea_half* __restrict__ add, int B, int H, int W, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float wsm[];  // [9*CIN][Cout] + bias[Cout]
+  const int nw = 9 * CIN * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[nw + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int ngrp = Cout >> 3;
+  const long long total = (long long)B * H * W * ngrp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % ngrp);
+    const long long pix = idx / ngrp;
+    const int wo = (int)(pix % W);
+    const int ho = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = wsm[nw + g * 8 + j];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho + kh - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo + kw - 1;
+        if (wi < 0 || wi >= W) continue;
+        const ea_half* xp = x + (((long long)b * H + hi) * W + wi) * CIN;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float xv = ea_h2f(xp[c]);
+          const float* wr = wsm + ((kh * 3 + kw) * CIN + c) * Cout + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+        }
+      }
+    }
+    if (add) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(add + pix * Cout + g * 8));
+      float2 a0 = ea_unpack2(u.x), a1 = ea_unpack2(u.y), a2 = ea_unpack2(u.z), a3 = ea_unpack2(u.w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+    const uint4 o = make_uint4(ea_pack2(acc[0], acc[1]), ea_pack2(acc[2], acc[3]),
+                               ea_pack2(acc[4], acc[5]), ea_pack2(acc[6], acc[7]));
+    *reinterpret_cast<uint4*>(out + pix * ldo + g * 8) = o;
+    if (out2) *reinterpret_cast<uint4*>(out2 + pix * ldo2 + g * 8) = o;
   }
 }
 
@@ -568,8 +651,7 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
     max_set = smem;
   }
   dim3 grid(chunks, a->B);
-  gn_fused_kernel<<<grid, threads, smem, st>>>(
-      reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
+  ea_launch(gn_fused_kernel, dim3(grid), dim3(threads), (size_t)(smem), st, reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
       a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
       a->groups, a->eps, a->silu, chunks, ppc, cached, a->workspace);
   return EA_LAUNCH_OK();
@@ -580,8 +662,7 @@ extern "C" int ea_layernorm(const void* x, long long ldx, const float* gamma, co
   if (!x || !out || !gamma || !beta) return EA_ERR_ARG;
   if (C % 8 != 0 || C > 8 * 32 * LN_MAXV || ldx % 8 != 0 || ldo % 8 != 0) return EA_ERR_SHAPE;
   const int wpc = 8;
-  layernorm_kernel<<<(M + wpc - 1) / wpc, wpc * 32, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(x), ldx, gamma, beta, reinterpret_cast<ea_half*>(out), ldo,
+  ea_launch(layernorm_kernel, dim3((M + wpc - 1) / wpc), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), ldx, gamma, beta, reinterpret_cast<ea_half*>(out), ldo,
       M, C, eps);
   return EA_LAUNCH_OK();
 }
@@ -593,8 +674,7 @@ extern "C" int ea_conv_direct(const void* x, const float* w, const float* bias, 
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EA_ERR_SHAPE;
   int Ho = (Hin + stride - 1) / stride, Wo = (Win + stride - 1) / stride;
   long long total = (long long)B * Ho * Wo * Cout;
-  conv_direct_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(x), w, bias, reinterpret_cast<ea_half*>(out), B, Hin, Win,
+  ea_launch(conv_direct_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), w, bias, reinterpret_cast<ea_half*>(out), B, Hin, Win,
       Cin, Cout, ksize, stride, silu, reinterpret_cast<const ea_half*>(add), ldo > 0 ? ldo : Cout);
   return EA_LAUNCH_OK();
 }
@@ -603,8 +683,7 @@ extern "C" int ea_upsample2x(const void* x, void* out, int B, int H, int W, int 
   if (!x || !out) return EA_ERR_ARG;
   if (C % 8 != 0) return EA_ERR_SHAPE;
   long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C);
+  ea_launch(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C);
   return EA_LAUNCH_OK();
 }
 
@@ -613,8 +692,7 @@ extern "C" int ea_small_linear(const float* x, const void* w, const float* bias,
   if (!x || !w || !y) return EA_ERR_ARG;
   if (M < 1 || M > 16 || K % 8 != 0) return EA_ERR_SHAPE;
   const int wpc = 8;
-  small_linear_kernel<<<(N + wpc - 1) / wpc, wpc * 32, 0, EA_STREAM(stream)>>>(
-      x, reinterpret_cast<const ea_half*>(w), bias, y, M, N, K, silu_in, silu_out);
+  ea_launch(small_linear_kernel, dim3((N + wpc - 1) / wpc), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), x, reinterpret_cast<const ea_half*>(w), bias, y, M, N, K, silu_in, silu_out);
   return EA_LAUNCH_OK();
 }
 
@@ -622,7 +700,7 @@ extern "C" int ea_timestep_embedding(const float* t, float* out, int B, int dim,
   if (!t || !out) return EA_ERR_ARG;
   if (dim % 2 != 0) return EA_ERR_SHAPE;
   int total = B * dim / 2;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, EA_STREAM(stream)>>>(t, out, B, dim);
+  ea_launch(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), (size_t)(0), EA_STREAM(stream), t, out, B, dim);
   return EA_LAUNCH_OK();
 }
 
@@ -636,8 +714,7 @@ extern "C" int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias
   if (C % 8 != 0) return EA_ERR_SHAPE;
   long long npix = (long long)Nimg * H * W;
   const int wpc = 4;
-  out_cfg_ddim_kernel<<<(unsigned)((npix + wpc - 1) / wpc), wpc * 32, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, mask,
+  ea_launch(out_cfg_ddim_kernel, dim3((unsigned)((npix + wpc - 1) / wpc)), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, mask,
       reinterpret_cast<ea_half*>(lat_half_out), Nimg, H, W, C);
   return EA_LAUNCH_OK();
 }
@@ -648,8 +725,7 @@ extern "C" int ea_sam_relpos(const void* q, long long q_bs, long long q_ns, cons
   if (!q || !Rh || !Rw || !rel_h || !rel_w) return EA_ERR_ARG;
   if (d % 2 != 0) return EA_ERR_SHAPE;
   long long total = (long long)B * heads * S * S * 2 * S;
-  sam_relpos_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(q), q_bs, q_ns, Rh, Rw, rel_h, rel_w, B, heads, S, d);
+  ea_launch(sam_relpos_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(q), q_bs, q_ns, Rh, Rw, rel_h, rel_w, B, heads, S, d);
   return EA_LAUNCH_OK();
 }
 
@@ -659,8 +735,7 @@ extern "C" int ea_window_partition(const void* x, void* out, int B, int H, int W
   if (C % 8 != 0 || ws <= 0) return EA_ERR_SHAPE;
   int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
   long long total = (long long)B * nWh * nWw * ws * ws * (C / 8);
-  window_partition_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh,
+  ea_launch(window_partition_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh,
       nWw);
   return EA_LAUNCH_OK();
 }
@@ -671,8 +746,7 @@ extern "C" int ea_window_unpartition(const void* xw, const void* residual, void*
   if (C % 8 != 0 || ws <= 0) return EA_ERR_SHAPE;
   int nWh = (H + ws - 1) / ws, nWw = (W + ws - 1) / ws;
   long long total = (long long)B * H * W * (C / 8);
-  window_unpartition_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(xw), reinterpret_cast<const ea_half*>(residual),
+  ea_launch(window_unpartition_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(xw), reinterpret_cast<const ea_half*>(residual),
       reinterpret_cast<ea_half*>(out), B, H, W, C, ws, nWh, nWw);
   return EA_LAUNCH_OK();
 }
@@ -682,15 +756,52 @@ extern "C" int ea_sam_patchify(const float* img, void* out, int B, int Cin, int 
   if (!img || !out) return EA_ERR_ARG;
   if (ps % 8 != 0 || H % ps != 0 || W % ps != 0 || W % 4 != 0) return EA_ERR_SHAPE;
   long long total = (long long)B * (H / ps) * (W / ps) * (Cin * ps * ps / 8);
-  patchify_kernel<<<grid_for(total, 256), 256, 0, EA_STREAM(stream)>>>(
-      img, reinterpret_cast<ea_half*>(out), B, Cin, H, W, ps);
+  ea_launch(patchify_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), img, reinterpret_cast<ea_half*>(out), B, Cin, H, W, ps);
   return EA_LAUNCH_OK();
 }
 
 extern "C" int ea_nhwc_to_nchw_f32(const void* x, float* out, int B, int HW, int C, void* stream) {
   if (!x || !out) return EA_ERR_ARG;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nhwc_to_nchw_f32_kernel<<<grid, block, 0, EA_STREAM(stream)>>>(
-      reinterpret_cast<const ea_half*>(x), out, B, HW, C);
+  ea_launch(nhwc_to_nchw_f32_kernel, dim3(grid), dim3(block), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), out, B, HW, C);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_conv_in(const void* x, const float* w, const float* bias, void* out, long long ldo,
+                          void* out2, long long ldo2, const void* add, int B, int H, int W, int Cin,
+                          int Cout, void* stream) {
+  if (!x || !w || !out) return EA_ERR_ARG;
+  if (Cout % 8 != 0 || (Cin != 4 && Cin != 8) || ldo % 8 != 0 || (out2 && ldo2 % 8 != 0))
+    return EA_ERR_SHAPE;
+  const int smem = (9 * Cin * Cout + Cout) * (int)sizeof(float);
+  const long long total = (long long)B * H * W * (Cout / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid < 1) grid = 1;
+  cudaStream_t st = EA_STREAM(stream);
+  const ea_half* xx = reinterpret_cast<const ea_half*>(x);
+  ea_half* o1 = reinterpret_cast<ea_half*>(out);
+  ea_half* o2 = reinterpret_cast<ea_half*>(out2);
+  const ea_half* ad = reinterpret_cast<const ea_half*>(add);
+  const long long l1 = ldo > 0 ? ldo : Cout, l2 = ldo2 > 0 ? ldo2 : Cout;
+  if (Cin == 4) {
+    static bool set4 = false;
+    if (!set4) {
+      if (cudaFuncSetAttribute(conv_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               96 * 1024) != cudaSuccess) return EA_ERR_CUDA;
+      set4 = true;
+    }
+    if (smem > 96 * 1024) return EA_ERR_SHAPE;
+    ea_launch(conv_smallcin_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, xx, w, bias, o1, l1, o2, l2, ad, B, H, W, Cout);
+  } else {
+    static bool set8 = false;
+    if (!set8) {
+      if (cudaFuncSetAttribute(conv_smallcin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               192 * 1024) != cudaSuccess) return EA_ERR_CUDA;
+      set8 = true;
+    }
+    if (smem > 192 * 1024) return EA_ERR_SHAPE;
+    ea_launch(conv_smallcin_kernel<8>, dim3(grid), dim3(256), (size_t)(smem), st, xx, w, bias, o1, l1, o2, l2, ad, B, H, W, Cout);
+  }
   return EA_LAUNCH_OK();
 }

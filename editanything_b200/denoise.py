@@ -84,10 +84,27 @@ class DenoiseEngine:
             self._graph = None        # scales are baked into the zero-conv launches
         self.scales = new_scales
         if not hasattr(self, "t_dev") or self.t_dev.shape[0] != self.B:
+            self._emb_cache = {}
+            nets = [self.unet] + self.cns
+            self.emb_bufs = [torch.zeros(self.B, n.emb_total, device=self.dev, dtype=torch.float32) for n in nets]
             self.t_dev = torch.zeros(self.B, device=self.dev, dtype=torch.float32)
             self.coef_dev = torch.zeros(4, device=self.dev, dtype=torch.float32)
             self.gn_ws = torch.zeros(self.B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
             self._graph = None
+
+    def _fill_emb(self, t):
+        """Time-embedding rows for timestep t into the fixed buffers the (captured) step reads.
+        Computed once per distinct t (util.py:154-174 + time_embed + every ResBlock emb_layers,
+        openaimodel.py:526-531,204-210) and cached: the DDIM table repeats for every image."""
+        key = float(t)
+        rows = self._emb_cache.get(key)
+        if rows is None:
+            self.t_dev.fill_(key)
+            rows = [e.clone() for e in self.runner.compute_embs(self.t_dev, self.B)]
+            if len(self._emb_cache) < 1100:
+                self._emb_cache[key] = rows
+        for buf, r in zip(self.emb_bufs, rows):
+            buf.copy_(r)
 
     # -- parity API: the network output itself ------------------------------------------------
     def eps(self, x_nchw, t):
@@ -95,8 +112,9 @@ class DenoiseEngine:
         NCHW — the quantity the reference calls `noise_pred` before guidance."""
         B, C, H, W_ = x_nchw.shape
         xh = x_nchw.to(self.dev).permute(0, 2, 3, 1).contiguous().to(self.hdt)
-        self.t_dev.fill_(float(t))
-        xn = self.runner.eps_features(xh, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws)
+        self._fill_emb(t)
+        xn = self.runner.eps_features(xh, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws,
+                                      embs=self.emb_bufs)
         eps = torch.empty(B, H, W_, 4, device=self.dev, dtype=torch.float32)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], eps_out=eps, Nimg=B // 2, H=H,
                               W=W_, C_=self.cfg.model_channels)
@@ -105,7 +123,8 @@ class DenoiseEngine:
     # -- production API: one fused denoising step ----------------------------------------------
     def _step_body(self):
         H, W_ = self.lat.shape[1], self.lat.shape[2]
-        xn = self.runner.eps_features(self.x_half, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws)
+        xn = self.runner.eps_features(self.x_half, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws,
+                                      embs=self.emb_bufs)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], latents=self.lat,
                               coef=self.coef_dev, guidance=self.guidance, known=self.known, mask=self.mask,
                               lat_half_out=self.x_half, Nimg=self.B // 2, H=H, W=W_, C_=self.cfg.model_channels)
@@ -137,7 +156,7 @@ class DenoiseEngine:
 
     def step(self, t, a_t, a_prev):
         """One DDIM (eta=0) step at timestep t (cldm/ddim_hacked.py:181-231)."""
-        self.t_dev.fill_(float(t))
+        self._fill_emb(t)
         self.coef_dev.copy_(torch.tensor([math.sqrt(a_t), math.sqrt(1.0 - a_t), math.sqrt(a_prev),
                                           math.sqrt(1.0 - a_prev)], dtype=torch.float32), non_blocking=True)
         if not self._use_graph:

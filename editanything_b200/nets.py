@@ -305,11 +305,16 @@ class UNetRunner:
             if layers[0].kind == "conv_in":
                 blk = layers[0]
                 h = net._new(B, H, W_, blk.cout)
-                o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], h, B=B, Hin=H, Win=W_,
-                              Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, add=guided_hint)
-                if is_unet:
-                    o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], slot, B=B, Hin=H, Win=W_,
-                                  Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, ldo=slot.stride(2))
+                if blk.cin in (4, 8):
+                    o.conv_in(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], h, B=B, H=H, W=W_, Cin=blk.cin,
+                              Cout=blk.cout, out2=slot if is_unet else None,
+                              ldo2=slot.stride(2) if is_unet else 0, add=guided_hint)
+                else:
+                    o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], h, B=B, Hin=H, Win=W_,
+                                  Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, add=guided_hint)
+                    if is_unet:
+                        o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], slot, B=B, Hin=H, Win=W_,
+                                      Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, ldo=slot.stride(2))
             else:
                 h = net._run_layers(layers, h, emb_all, ctxc, gn_ws, final_out2=slot if is_unet else None)
             if not is_unet:
@@ -352,7 +357,13 @@ class UNetRunner:
         mid = cats[0][0][..., :cats[0][1]]  # mid output IS the h-part of the first decoder concat
         return {"cats": cats, "skip": skip_slots, "mid": mid}
 
-    def eps_features(self, x_half, t_dev, ctx_cache, hints, scales, gn_ws=None):
+    def compute_embs(self, t_dev, B):
+        """Per-ResBlock time-embedding projections of every net for timestep(s) t_dev: a list of
+        [B, emb_total] fp32 tensors (UNet first).  They depend on t only, so the engine caches them
+        per timestep instead of re-streaming ~93 MB of embedding weights every step."""
+        return [n._emb(t_dev, B) for n in [self.unet] + self.cns]
+
+    def eps_features(self, x_half, t_dev, ctx_cache, hints, scales, gn_ws=None, embs=None):
         """Runs UNet encoder, ControlNets, UNet decoder; returns the GroupNorm+SiLU'd input of the
         final convolution [B,H,W,mc] (the out conv itself is fused with CFG/DDIM)."""
         un = self.unet
@@ -361,10 +372,12 @@ class UNetRunner:
         if gn_ws is None:
             gn_ws = torch.zeros(B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
         sinks = self.alloc_sinks(B, H, W_)
-        emb_u = un._emb(t_dev, B)
+        if embs is None:
+            embs = self.compute_embs(t_dev, B)
+        emb_u = embs[0]
         self._encoder(un, x_half, emb_u, ctx_cache[0], gn_ws, sinks=sinks)
         for k, cn in enumerate(self.cns):
-            emb_c = cn._emb(t_dev, B)
+            emb_c = embs[1 + k]
             self._encoder(cn, x_half, emb_c, ctx_cache[1 + k], gn_ws, guided_hint=hints[k], sinks=sinks,
                           scale=float(scales[k]))
         topo = un.topo

@@ -161,6 +161,14 @@ def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, s
     return out
 
 
+def conv_in(x, w, bias, out, *, B, H, W, Cin, Cout, out2=None, add=None, ldo=0, ldo2=0):
+    """w: fp32 [3, 3, Cin, Cout]; out2 = optional second destination, add = optional dense addend."""
+    lib = L.lib()
+    L.check(lib.ea_conv_in(_p(x), _p(w), _p(bias), _p(out), ldo, _p(out2), ldo2, _p(add), B, H, W, Cin, Cout,
+                           _stream()), "ea_conv_in")
+    return out
+
+
 def upsample2x(x, out, *, B, H, W, C_):
     lib = L.lib()
     L.check(lib.ea_upsample2x(_p(x), _p(out), B, H, W, C_, _stream()), "ea_upsample2x")

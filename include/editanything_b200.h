@@ -43,6 +43,8 @@ const char* ea_dtype_name(void);      /* "float16" | "bfloat16" */
 const char* ea_strerror(int status);
 int ea_init(void);                    /* resolves cuTensorMapEncodeTiled; 0 on success */
 long long ea_launch_count(void);      /* kernels launched by this library since reset */
+void ea_set_pdl(int on);              /* programmatic dependent launch between consecutive kernels
+                                         (default on; env EA_PDL=0 disables) */
 void ea_reset_launch_count(void);
 
 /* ---- ea_gemm: tcgen05 GEMM / implicit-GEMM convolution ------------------------------------
@@ -107,6 +109,10 @@ typedef struct ea_gemm_args {
                                 is never split.  One workspace may serve every call on a stream. */
 } ea_gemm_args;
 int ea_gemm(const ea_gemm_args* args, void* stream);
+/* Diagnostic (no GPU needed): the launch plan ea_gemm would choose for m_tiles x N with k_blocks
+ * 64-wide K-blocks: out5 = {BN, stages, splits, k_blocks_per_split, CTAs_per_SM}. */
+int ea_gemm_plan(int m_tiles, int N, int k_blocks, int act, long long workspace_bytes, int n_sm,
+                 int* out5);
 
 /* ---- ea_attention: fused softmax(Q K^T * scale [+ rel-pos bias]) V -------------------------
  * Replaces CrossAttention.forward core  ldm/modules/attention.py:170-193 (QK^T in fp32,
@@ -162,6 +168,13 @@ int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* 
 int ea_conv_direct(const void* x, const float* w, const float* bias, void* out, int B, int Hin,
                    int Win, int Cin, int Cout, int ksize, int stride, int silu,
                    const void* add, long long ldo, void* stream);
+/* ea_conv_in: 3x3 stride-1 pad-1 conv with Cin in {4, 8} (UNet / ControlNet conv_in 4->320,
+ *   openaimodel.py:533-539): x NHWC half [B,H,W,Cin], w fp32 [3,3,Cin,Cout], out NHWC half with pixel
+ *   stride ldo (0 -> Cout); out2 (optional) receives the same values (UNet skip-concat slot); add
+ *   (optional) dense half [B,H,W,Cout] added before the store (ControlNet guided hint, cldm/cldm.py:293-297). */
+int ea_conv_in(const void* x, const float* w, const float* bias, void* out, long long ldo,
+               void* out2, long long ldo2, const void* add, int B, int H, int W, int Cin, int Cout,
+               void* stream);
 int ea_upsample2x(const void* x, void* out, int B, int H, int W, int C, void* stream);
 int ea_small_linear(const float* x, const void* w, const float* bias, float* y, int M, int N,
                     int K, int silu_in, int silu_out, void* stream);

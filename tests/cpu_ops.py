@@ -122,6 +122,17 @@ def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, s
     return out
 
 
+def conv_in(x, w, bias, out, *, B, H, W, Cin, Cout, out2=None, add=None, ldo=0, ldo2=0):
+    _bump()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    out.copy_(y)
+    if out2 is not None:
+        out2.copy_(y)
+    return out
+
+
 def upsample2x(x, out, *, B, H, W, C_):
     _bump()
     out.copy_(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1))

@@ -14,6 +14,8 @@ from editanything_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    iters = int(os.environ.get("EA_BENCH_ITERS", iters))
+    warm = int(os.environ.get("EA_BENCH_WARM", warm))
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()

@@ -400,6 +400,27 @@ def case_small_ops():
     return r
 
 
+def case_conv_in():
+    import torch
+    import torch.nn.functional as F
+    from editanything_b200 import ops
+    dt = ops.half_dtype()
+    torch.manual_seed(13)
+    x = torch.randn(2, 4, 64, 64, device="cuda").to(dt)
+    w = torch.randn(320, 4, 3, 3, device="cuda") * 0.2
+    b = torch.randn(320, device="cuda")
+    add = torch.randn(2, 64, 64, 320, device="cuda").to(dt)
+    out = torch.empty(2, 64, 64, 320, device="cuda", dtype=dt)
+    cat = torch.zeros(2, 64, 64, 640, device="cuda", dtype=dt)
+    ops.conv_in(x.permute(0, 2, 3, 1).contiguous(), w.permute(2, 3, 1, 0).contiguous(), b, out, B=2, H=64, W=64, Cin=4,
+                Cout=320, out2=cat[..., 320:], ldo2=640, add=add)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w, b, padding=1).permute(0, 2, 3, 1) + add.float()
+    e1, e2 = _err(out, ref), _err(cat[..., 320:], ref)
+    return {"max_abs": max(e1["max_abs"], e2["max_abs"]) / max(1.0, e1["ref_max"]), "ref_max": 1.0,
+            "left_untouched": float(cat[..., :320].abs().max().item())}
+
+
 def case_out_cfg_ddim():
     import torch
     import torch.nn.functional as F
