@@ -231,6 +231,21 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const Row
   }
 }
 
+#ifdef EA_GEMM_TIMING
+// Experiment build only: clock64 stamps of CTA (0,0,0): producer (slot 0: stage free, 1: TMA issued)
+// and MMA thread (2: operands landed, 3: MMAs + commit issued) for the first 64 K-blocks; slot 4/5 =
+// kernel entry / setup done, 6 = accumulator complete (epilogue start), 7 = epilogue done.
+__device__ long long ea_gemm_dbg[64 * 4 + 8];
+#define EA_GT(idx, slot) do { if (dbg_cta && (idx) < 64) ea_gemm_dbg[(idx) * 4 + (slot)] = clock64(); } while (0)
+#define EA_GT1(slot) do { if (dbg_cta) ea_gemm_dbg[256 + (slot)] = clock64(); } while (0)
+#else
+#define EA_GT(idx, slot) do {} while (0)
+#define EA_GT1(slot) do {} while (0)
+#endif
+
+// TWO = true: CTA pairs (cluster of 2 along M) run tcgen05.mma.cta_group::2 with M = 256; each CTA
+// stages its own A tile and HALF of the B tile (rows tn*BN + rank*BN/2 ...), the leader issues.
+template <bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
@@ -241,8 +256,10 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int a_bytes = BM * BK * 2;
-  const int b_bytes = p.BN * BK * 2;
+  const int b_rows = TWO ? (p.BN >> 1) : p.BN;     // B rows staged by THIS CTA
+  const int b_bytes = b_rows * BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -253,6 +270,10 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int tm = blockIdx.x;
   const int tn = blockIdx.y;
+#ifdef EA_GEMM_TIMING
+  const bool dbg_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (threadIdx.x == 0) EA_GT1(0);
+#endif
   const int nkb_total = p.nkb_main + p.nkb_extra;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + p.kb_per_split);
@@ -276,13 +297,18 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == W_MMA) {
-    tmem_alloc(tmem_slot, tmem_cols_for(p.BN));
+    if (TWO) tmem_alloc_2cta(tmem_slot, tmem_cols_for(p.BN));
+    else tmem_alloc(tmem_slot, tmem_cols_for(p.BN));
   }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail
+#ifdef EA_GEMM_TIMING
+  if (threadIdx.x == 0) EA_GT1(1);
+#endif
 
   if (warp == W_TMA) {
     // ============================ TMA producer ============================
@@ -294,15 +320,25 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.mode != EA_GEMM_LINEAR) tile_origin(p, tm, n0, h0, w0);
       int stage = 0;
       uint32_t phase = 0;
-      const int bcol = tn * p.BN;
+      const int bcol = tn * p.BN + (int)rank * b_rows;
       uint8_t* sa = smem;
+      // TWO: both CTAs signal the LEADER's full barrier (it expects both CTAs' bytes)
+      const uint32_t full0 = TWO ? mapa_shared(smem_u32(&full_bar[0]), 0u) : 0u;
+      const uint32_t tx_bytes = TWO ? 2u * (uint32_t)stage_bytes : (uint32_t)stage_bytes;
       if (p.mode == EA_GEMM_LINEAR) {
         const int arow = tm * BM;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, arow);
-          tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+          EA_GT(kb - kb0, 0);
+          if (!TWO || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (TWO) {
+            tma_load_2d_2cta(sa, &tmA0, full0 + 8u * stage, kb * BK, arow);
+            tma_load_2d_2cta(sa + a_bytes, &tmB, full0 + 8u * stage, kb * BK, bcol);
+          } else {
+            tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, arow);
+            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+          }
+          EA_GT(kb - kb0, 1);
           sa += stage_bytes;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; sa = smem; }
         }
@@ -314,8 +350,13 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int cin = p.cin_blocks * BK;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          if (kb >= p.nkb_main) {
+          if (!TWO || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (TWO) {
+            const uint32_t fb = full0 + 8u * stage;
+            if (kb >= p.nkb_main) tma_load_4d_2cta(sa, &tmAx, fb, (kb - p.nkb_main) * BK, w0, h0, n0);
+            else tma_load_4d_2cta(sa, &tmA0, fb, c0, w0 + kw - 1, h0 + kh - 1, n0);   // CONV_S1 only
+            tma_load_2d_2cta(sa + a_bytes, &tmB, fb, kb * BK, bcol);
+          } else if (kb >= p.nkb_main) {
             // fused 1x1 skip convolution: centre tap of the raw block input
             tma_load_4d(sa, &tmAx, &full_bar[stage], (kb - p.nkb_main) * BK, w0, h0, n0);
           } else if (p.mode == EA_GEMM_CONV_S1) {
@@ -328,7 +369,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
             tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
           }
-          tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+          if (!TWO) tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
           c0 += BK;
           if (c0 == cin) { c0 = 0; if (++kw == 3) { kw = 0; ++kh; } }
           sa += stage_bytes;
@@ -339,8 +380,8 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == W_MMA) {
     // ============================ MMA issuer ==============================
     // One thread; descriptors are advanced with 32-bit adds on the 16-byte-unit address field.
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BM, (uint32_t)p.BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc(TWO ? 2 * BM : BM, (uint32_t)p.BN, 0, 0);
       const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem), 1024);   // stage 0, A tile
       const uint32_t st16 = (uint32_t)stage_bytes >> 4, ab16 = (uint32_t)a_bytes >> 4;
       uint64_t da = d0;
@@ -350,17 +391,28 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        EA_GT(kb - kb0, 2);
         const uint64_t db = da + ab16;
-        umma_f16_ss(tmem_base, da, db, idesc, acc);
-        umma_f16_ss(tmem_base, da + 2, db + 2, idesc, 1u);
-        umma_f16_ss(tmem_base, da + 4, db + 4, idesc, 1u);
-        umma_f16_ss(tmem_base, da + 6, db + 6, idesc, 1u);
+        if (TWO) {
+          umma_f16_ss_2cta(tmem_base, da, db, idesc, acc);
+          umma_f16_ss_2cta(tmem_base, da + 2, db + 2, idesc, 1u);
+          umma_f16_ss_2cta(tmem_base, da + 4, db + 4, idesc, 1u);
+          umma_f16_ss_2cta(tmem_base, da + 6, db + 6, idesc, 1u);
+          umma_commit_2cta(&empty_bar[stage], (uint16_t)3);  // frees the stage in BOTH CTAs
+        } else {
+          umma_f16_ss(tmem_base, da, db, idesc, acc);
+          umma_f16_ss(tmem_base, da + 2, db + 2, idesc, 1u);
+          umma_f16_ss(tmem_base, da + 4, db + 4, idesc, 1u);
+          umma_f16_ss(tmem_base, da + 6, db + 6, idesc, 1u);
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        }
         acc = 1u;
-        umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        EA_GT(kb - kb0, 3);
         da += st16;
         if (++stage == p.stages) { stage = 0; phase ^= 1u; da = d0; }
       }
-      umma_commit(tmem_full_bar);
+      if (TWO) umma_commit_2cta(tmem_full_bar, (uint16_t)3);
+      else umma_commit(tmem_full_bar);
     }
   } else {
     // ============================== epilogue ==============================
@@ -370,6 +422,9 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     RowInfo ri = row_info(p, tm, r);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+#ifdef EA_GEMM_TIMING
+    if (threadIdx.x == 0) EA_GT1(6);
+#endif
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     const int ncol0 = tn * p.BN;
     const bool geglu = p.act == EA_ACT_GEGLU;
@@ -507,11 +562,16 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
 
+#ifdef EA_GEMM_TIMING
+  if (threadIdx.x == 0) EA_GT1(7);
+#endif
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the end
   if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols_for(p.BN));
+    if (TWO) tmem_dealloc_2cta(tmem_base, tmem_cols_for(p.BN));
+    else tmem_dealloc(tmem_base, tmem_cols_for(p.BN));
   }
 }
 
@@ -557,13 +617,49 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // needs max(MMA time, its share of chip bandwidth, TMA latency / stages in flight); small-M layers
 // (8x8 / 16x16 latents: M = 128 / 512) are weight-streaming bound, so K is split across CTAs until
 // every SM has one deep pipeline, and the partial tiles are combined in-kernel (see the epilogue).
-struct GemmPlan { int BN, stages, splits, kbps, occ; double cost; };
+struct GemmPlan { int BN, stages, splits, kbps, occ; double cost; int two; };
 
-static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm) {
+static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm,
+                          bool allow_two) {
   // measured on B200 (profiles/r01c): one SM fills shared memory at ~45 B/clk whatever the tile
   // shape (cuBLAS sits at the same cap with 2-CTA 256x256 tiles), the chip at ~6000 B/clk from L2
   // and ~3400 B/clk from HBM; a tcgen05 128xBNx16 MMA takes BN/2 clk.
-  GemmPlan best = {0, 0, 1, nkb, 1, 1e30};
+  GemmPlan best = {0, 0, 1, nkb, 1, 1e30, 0};
+  // CTA pairs (cta_group::2): per SM the TMA stream per K-block shrinks from 16 KB + BN*128 B to
+  // 16 KB + BN*64 B for the same 128 x BN MACs.  Only without split-K and for stride-1 shapes.
+  if (allow_two && mt >= 2) {
+    for (int BN = 256; BN >= 64; BN -= 32) {
+      if (act == EA_ACT_GEGLU && BN != 128) continue;
+      if (N <= BN - 32) continue;
+      const int nt = (N + BN - 1) / BN;
+      const int mt2 = (mt + 1) / 2 * 2;
+      const long long ctas = (long long)mt2 * nt;
+      const int stage_bytes = BM * BK * 2 + (BN / 2) * BK * 2;
+      const int tmem = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+      for (int occ = 2; occ >= 1; --occ) {
+        if (occ * tmem > 512) continue;
+        const int avail = (occ == 2 ? 111 : 224) * 1024 - 2048;
+        int st = avail / stage_bytes;
+        if (st > 8) st = 8;
+        if (st > nkb) st = nkb < 2 ? 2 : nkb;
+        if (st < 2 || (occ == 2 && st < 3 && nkb >= 3)) continue;
+        const long long slots = (long long)n_sm * occ;
+        const long long waves = (ctas + slots - 1) / slots;
+        const long long conc = ctas < slots ? ctas : slots;
+        const int per_sm = (int)((conc + n_sm - 1) / n_sm);
+        const double t_mma = 0.5 * BN * 4 * per_sm;
+        const double t_sm = (double)stage_bytes * per_sm / 52.0;
+        const double t_chip = (double)conc * stage_bytes / 6000.0;
+        const double t_lat = 1800.0 / st;
+        double t_kb = t_mma;
+        if (t_sm > t_kb) t_kb = t_sm;
+        if (t_chip > t_kb) t_kb = t_chip;
+        if (t_lat > t_kb) t_kb = t_lat;
+        const double cost = (double)waves * (nkb * t_kb + 4200.0 + 8.0 * BN);
+        if (cost < best.cost) best = {BN, st, 1, nkb, occ, cost, 1};
+      }
+    }
+  }
   for (int BN = 256; BN >= 32; BN -= 32) {
     if (act == EA_ACT_GEGLU && BN != 128) continue;  // weights are interleaved per 128-row block
     if (BN > 32 && N <= BN - 32) continue;            // a narrower tile covers N just as well
@@ -596,7 +692,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
         const long long conc = ctas < slots ? ctas : slots;
         const int per_sm = (int)((conc + n_sm - 1) / n_sm);
         const double t_mma = 0.5 * BN * 4 * per_sm;                       // 4 MMAs (K=16) per K-block
-        const double t_sm = (double)stage_bytes * per_sm / 45.0;          // per-SM smem fill cap
+        const double t_sm = (double)stage_bytes * per_sm / 52.0;          // per-SM TMA fill cap
         const double a_bytes = BM * BK * 2.0, b_bytes = BN * BK * 2.0;
         const double hbm_frac = 1.0 / (double)mt;                         // weights: HBM once, then L2
         const double t_chip = (double)conc * (a_bytes / 6000.0 + b_bytes * hbm_frac / 3400.0 +
@@ -608,7 +704,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
         if (t_lat > t_kb) t_kb = t_lat;
         double cost = (double)waves * (kbps * t_kb + 3500.0 + 8.0 * BN);
         if (splits > 1) cost += 2500.0 + 2.0 * (BM * BN * 4.0) / 25.0;   // partial store + reduce
-        if (cost < best.cost) best = {BN, st, splits, kbps, occ, cost};
+        if (cost < best.cost) best = {BN, st, splits, kbps, occ, cost, 0};
       }
     }
   }
@@ -632,12 +728,20 @@ static int sm_count() {
 
 using namespace ea;
 
+#ifdef EA_GEMM_TIMING
+extern "C" int ea_gemm_debug_read(long long* host_out, int n) {
+  if (n > 64 * 4 + 8) n = 64 * 4 + 8;
+  return cudaMemcpyFromSymbol(host_out, ea_gemm_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : EA_ERR_CUDA;
+}
+#endif
+
 extern "C" int ea_gemm_plan(int m_tiles, int N, int k_blocks, int act, long long workspace_bytes,
                             int n_sm, int* out5) {
   if (!out5 || m_tiles <= 0 || N <= 0 || k_blocks <= 0) return EA_ERR_ARG;
   const long long ws_floats = workspace_bytes > 65536 ? (workspace_bytes - 65536) / 4 : 0;
-  GemmPlan pl = plan_gemm(m_tiles, N, k_blocks, act, ws_floats, n_sm > 0 ? n_sm : 148);
-  out5[0] = pl.BN; out5[1] = pl.stages; out5[2] = pl.splits; out5[3] = pl.kbps; out5[4] = pl.occ;
+  GemmPlan pl = plan_gemm(m_tiles, N, k_blocks, act, ws_floats, n_sm > 0 ? n_sm : 148, true);
+  out5[0] = pl.BN; out5[1] = pl.stages; out5[2] = pl.splits; out5[3] = pl.kbps;
+  out5[4] = pl.occ + 10 * pl.two;   // tens digit: 1 = CTA pairs (cta_group::2)
   return pl.BN ? EA_OK : EA_ERR_SHAPE;
 }
 
@@ -734,7 +838,14 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   // workspace: [0, 64 KB) arrival counters (int, zero between launches), then fp32 partial tiles
   const long long ws_floats =
       (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
-  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count());
+  static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
+  const bool can_two = a->mode != EA_GEMM_CONV_S2 && two_env != 0 && a->force_2cta >= 0;
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two);
+  if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
+    plan.two = 1; plan.splits = 1; plan.kbps = nkb;
+    if (plan.BN < 64) plan.BN = 64;
+    plan.stages = 3;
+  }
   if (a->force_bn > 0 || a->force_stages > 0 || a->force_splits > 0) {
     if (a->force_bn > 0) plan.BN = a->force_bn;
     const int sb = BM * BK * 2 + plan.BN * BK * 2;
@@ -746,8 +857,11 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
     if (a->force_splits > 1) {
       plan.kbps = (nkb + a->force_splits - 1) / a->force_splits;
       plan.splits = (nkb + plan.kbps - 1) / plan.kbps;
+      plan.two = 0;
     }
+    if (a->force_2cta <= 0 && (a->force_bn > 0 || a->force_splits > 0)) plan.two = 0;
   }
+  const int two = plan.two && plan.splits == 1 && plan.BN >= 64 && plan.BN % 32 == 0;
   p.BN = plan.BN;
   if (p.BN < 32 || p.BN > 256 || p.BN % 32 != 0) return EA_ERR_ARG;
   if (a->act == EA_ACT_GEGLU && (a->N % 128 != 0 || p.BN != 128)) return EA_ERR_SHAPE;
@@ -765,25 +879,34 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   const long long ldw = a->ldw > 0 ? a->ldw : Ktot;
   if (ldw % 8 != 0) return EA_ERR_SHAPE;
   if (encode_2d(&tmB, a->w, (uint64_t)Ktot, (uint64_t)a->N, (uint64_t)ldw * 2, BK,
-                (uint32_t)p.BN))
+                (uint32_t)(two ? p.BN / 2 : p.BN)))
     return EA_ERR_TMAP;
 
-  const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+  const int stage_bytes = BM * BK * 2 + (two ? p.BN / 2 : p.BN) * BK * 2;
   int stages = plan.stages;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static int max_set = 0;
-  if (smem_bytes > max_set) {
-    if (cudaFuncSetAttribute(ea_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_bytes) != cudaSuccess)
-      return EA_ERR_CUDA;
-    max_set = smem_bytes;
+  static int max_set[2] = {0, 0};
+  if (smem_bytes > max_set[two]) {
+    cudaError_t se = two ? cudaFuncSetAttribute(ea_gemm_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                         : cudaFuncSetAttribute(ea_gemm_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (se != cudaSuccess) return EA_ERR_CUDA;
+    max_set[two] = smem_bytes;
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)p.splits);
-  cudaError_t le = ea_launch(ea_gemm_kernel, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream,
-                             tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p);
+  cudaError_t le;
+  if (two) {
+    dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, 1);   // whole CTA pairs along M
+    le = ea_launch_cluster(ea_gemm_kernel<true>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 2u,
+                           tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p);
+  } else {
+    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)p.splits);
+    le = ea_launch(ea_gemm_kernel<false>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream,
+                   tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p);
+  }
   ea_count_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
 }

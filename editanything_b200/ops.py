@@ -50,7 +50,7 @@ def gemm_workspace(device):
 def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
          conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
          out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
-         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0):
+         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0):
     """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes."""
     lib = L.lib()
     g = L.GemmArgs()
@@ -99,6 +99,7 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     g.force_bn = force_bn
     g.force_stages = force_stages
     g.force_splits = force_splits
+    g.force_2cta = force_2cta
     ws = gemm_workspace(a.device)
     g.workspace = ws.data_ptr()
     g.workspace_bytes = ws.numel()

@@ -103,6 +103,7 @@ typedef struct ea_gemm_args {
   int force_bn;              /* 0 = auto; else 32/64/128/256 (testing) */
   int force_stages;          /* 0 = auto */
   int force_splits;          /* 0 = auto; 1 = never split K; n = split K n ways (testing) */
+  int force_2cta;            /* 0 = auto; 1 = CTA pairs (tcgen05 cta_group::2, M = 256); -1 = never */
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K
