@@ -64,6 +64,7 @@ struct GemmKParams {
   // split-K: blockIdx.z = split index; partial tiles go through `ws`, arrival counters in `cnt`
   int splits;
   int kb_per_split;
+  int pair_release;  // stages are released to the producer two at a time (even stage count >= 4)
   float* ws;   // [tiles][splits][128][BN] fp32
   int* cnt;    // [tiles][2]: arrived, done (zero between launches)
 };
@@ -236,7 +237,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const Row
 // and MMA thread (2: operands landed, 3: MMAs + commit issued) for the first 64 K-blocks; slot 4/5 =
 // kernel entry / setup done, 6 = accumulator complete (epilogue start), 7 = epilogue done.
 __device__ long long ea_gemm_dbg[64 * 4 + 8];
-#define EA_GT(idx, slot) do { if (dbg_cta && (idx) < 64) ea_gemm_dbg[(idx) * 4 + (slot)] = clock64(); } while (0)
+#define EA_GT(idx, slot) do { if (dbg_cta && (idx) < 64 && (threadIdx.x & 31) == 0) ea_gemm_dbg[(idx) * 4 + (slot)] = clock64(); } while (0)
 #define EA_GT1(slot) do { if (dbg_cta) ea_gemm_dbg[256 + (slot)] = clock64(); } while (0)
 #else
 #define EA_GT(idx, slot) do {} while (0)
@@ -321,6 +322,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const int bcol = tn * p.BN + (int)rank * b_rows;
+      const bool pair_release = p.pair_release != 0;
       uint8_t* sa = smem;
       // TWO: both CTAs signal the LEADER's full barrier (it expects both CTAs' bytes)
       const uint32_t full0 = TWO ? mapa_shared(smem_u32(&full_bar[0]), 0u) : 0u;
@@ -328,7 +330,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.mode == EA_GEMM_LINEAR) {
         const int arow = tm * BM;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (!pair_release || !(stage & 1)) mbar_wait(&empty_bar[pair_release ? (stage | 1) : stage], phase ^ 1u);
           EA_GT(kb - kb0, 0);
           if (!TWO || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
           if (TWO) {
@@ -349,7 +351,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         int kh = tap / 3, kw = tap - kh * 3;
         const int cin = p.cin_blocks * BK;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (!pair_release || !(stage & 1)) mbar_wait(&empty_bar[pair_release ? (stage | 1) : stage], phase ^ 1u);
           if (!TWO || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
           if (TWO) {
             const uint32_t fb = full0 + 8u * stage;
@@ -380,10 +382,18 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == W_MMA) {
     // ============================ MMA issuer ==============================
     // One thread; descriptors are advanced with 32-bit adds on the 16-byte-unit address field.
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs this loop in warp-uniform control flow and one elected lane issues: the
+    // compiler then keeps the descriptors / addresses in uniform registers.  (Written as a
+    // single-lane branch the loop body compiled to ~110 scalar instructions per K-block with an
+    // ELECT/R2UR "waterfall" around every UTCHMMA, and this thread - not TMA or the tensor core -
+    // set the K-block rate at ~540 clk: tools/exp_gemm_timing.py, profiles/r01f.)
+    if (rank == 0) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = umma_idesc(TWO ? 2 * BM : BM, (uint32_t)p.BN, 0, 0);
       const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem), 1024);   // stage 0, A tile
       const uint32_t st16 = (uint32_t)stage_bytes >> 4, ab16 = (uint32_t)a_bytes >> 4;
+      const int stages = p.stages;
+      const bool pair_release = p.pair_release != 0;
       uint64_t da = d0;
       int stage = 0;
       uint32_t phase = 0;
@@ -393,26 +403,34 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         EA_GT(kb - kb0, 2);
         const uint64_t db = da + ab16;
-        if (TWO) {
-          umma_f16_ss_2cta(tmem_base, da, db, idesc, acc);
-          umma_f16_ss_2cta(tmem_base, da + 2, db + 2, idesc, 1u);
-          umma_f16_ss_2cta(tmem_base, da + 4, db + 4, idesc, 1u);
-          umma_f16_ss_2cta(tmem_base, da + 6, db + 6, idesc, 1u);
-          umma_commit_2cta(&empty_bar[stage], (uint16_t)3);  // frees the stage in BOTH CTAs
-        } else {
-          umma_f16_ss(tmem_base, da, db, idesc, acc);
-          umma_f16_ss(tmem_base, da + 2, db + 2, idesc, 1u);
-          umma_f16_ss(tmem_base, da + 4, db + 4, idesc, 1u);
-          umma_f16_ss(tmem_base, da + 6, db + 6, idesc, 1u);
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        const bool release = !pair_release || (stage & 1) || (kb + 1 == kb1);
+        uint64_t* ebar = &empty_bar[pair_release ? (stage | 1) : stage];
+        if (elect_one()) {
+          if (TWO) {
+            umma_f16_ss_2cta(tb, da, db, idesc, acc);
+            umma_f16_ss_2cta(tb, da + 2, db + 2, idesc, 1u);
+            umma_f16_ss_2cta(tb, da + 4, db + 4, idesc, 1u);
+            umma_f16_ss_2cta(tb, da + 6, db + 6, idesc, 1u);
+            if (release) umma_commit_2cta(ebar, (uint16_t)3);  // frees the stage(s) in BOTH CTAs
+          } else {
+            umma_f16_ss(tb, da, db, idesc, acc);
+            umma_f16_ss(tb, da + 2, db + 2, idesc, 1u);
+            umma_f16_ss(tb, da + 4, db + 4, idesc, 1u);
+            umma_f16_ss(tb, da + 6, db + 6, idesc, 1u);
+            if (release) umma_commit(ebar);  // frees the smem stage(s) when these MMAs retire
+          }
         }
+        __syncwarp();
         acc = 1u;
         EA_GT(kb - kb0, 3);
         da += st16;
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; da = d0; }
+        if (++stage == stages) { stage = 0; phase ^= 1u; da = d0; }
       }
-      if (TWO) umma_commit_2cta(tmem_full_bar, (uint16_t)3);
-      else umma_commit(tmem_full_bar);
+      if (elect_one()) {
+        if (TWO) umma_commit_2cta(tmem_full_bar, (uint16_t)3);
+        else umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
     }
   } else {
     // ============================== epilogue ==============================
@@ -886,7 +904,9 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   int stages = plan.stages;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
+  if (stages >= 5 && (stages & 1) && a->force_stages == 0) --stages;   // even: stages are released in pairs
   p.stages = stages;
+  p.pair_release = (stages >= 4 && stages % 2 == 0) ? 1 : 0;
   const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   static int max_set[2] = {0, 0};
   if (smem_bytes > max_set[two]) {

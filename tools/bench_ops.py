@@ -14,18 +14,40 @@ from editanything_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    """Average device time of fn() in microseconds.  The calls are captured into ONE CUDA graph and
+    the graph is replayed (the Python + ctypes + cuTensorMapEncode cost of a launch is ~25 us and
+    would otherwise hide every kernel faster than that)."""
     iters = int(os.environ.get("EA_BENCH_ITERS", iters))
     warm = int(os.environ.get("EA_BENCH_WARM", warm))
-    for _ in range(warm):
+    for _ in range(max(warm, 1)):
         fn()
+    torch.cuda.synchronize()
+    if os.environ.get("EA_BENCH_GRAPH", "1") == "0" or iters == 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3  # us
+    return e0.elapsed_time(e1) / (2 * iters) * 1e3  # us
 
 
 def bench_attn():
