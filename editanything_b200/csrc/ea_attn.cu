@@ -148,7 +148,13 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == W_MMA) {
     // ============================= MMA issuer =============================
-    if (lane == 0) {
+    // The whole warp runs the schedule in warp-uniform control flow and ONE elected lane issues
+    // (EA_ISSUE): descriptors and TMEM addresses then live in uniform registers.  As a single-lane
+    // branch every UTCHMMA was wrapped in an ELECT/R2UR waterfall and the 11 MMAs of a tile cost
+    // ~1100 clk to issue (tools/exp_attn_timing.py) - three times their execution time.
+#define EA_ISSUE(...) do { if (elect_one()) { __VA_ARGS__; } __syncwarp(); } while (0)
+    {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       // Issue loops are kept to a few scalar instructions per MMA (descriptor = base + small add):
       // a single thread retires about one dependent instruction per 4-5 cycles, and at d = 40 an
       // MMA itself only takes 24-64 cycles (measured: tools/exp/mma_rate2.cu).
@@ -166,7 +172,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       auto issue_S = [&](int t, int stage, uint32_t s_col) {
         uint64_t dq = dQ0 + (uint64_t)(t * q_tile16);
         uint64_t dk = dK0 + (uint64_t)(stage * kv_stage16);
-        const uint32_t d = tmem_base + s_col;
+        const uint32_t d = tb + s_col;
         umma_f16_ss(d, dq, dk, idesc_s, 0u);
         for (int ks = 1; ks < ksteps; ++ks) {
           const uint32_t step = (ks & 3) ? 2u : (uint32_t)((AT_ATOM >> 4) - 6);
@@ -178,7 +184,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // O_t += P_t(j) V_j ; P lives in TMEM columns p_col (16-bit pairs) or in smem tile t
       auto issue_PV = [&](int t, int stage, uint32_t p_col, uint32_t o_col, bool first) {
         uint64_t dv = dV0 + (uint64_t)(stage * kv_stage16);
-        const uint32_t d = tmem_base + o_col;
+        const uint32_t d = tb + o_col;
         uint32_t acc = first ? 0u : 1u;
         if (p_smem) {
           uint64_t dp = dP0 + (uint64_t)(t * (2 * AT_ATOM >> 4));
@@ -190,7 +196,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             dv += (16 * 128) >> 4;
           }
         } else {
-          uint32_t pa = tmem_base + p_col;
+          uint32_t pa = tb + p_col;
 #pragma unroll
           for (int ks = 0; ks < AT_BKV / 16; ++ks) {
             umma_f16_ts(d, pa, dv, idesc_o, acc);
@@ -205,10 +211,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // stage/phase of K/V tile j
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        issue_S(0, 0, 0);
-        umma_commit(&s_full[0]);
-        issue_S(1, 0, 128);
-        umma_commit(&s_full[1]);
+        EA_ISSUE(issue_S(0, 0, 0); umma_commit(&s_full[0]); issue_S(1, 0, 128); umma_commit(&s_full[1]));
         int stage = 0;
         uint32_t phase = 0;
         for (int j = 0; j < n_tiles; ++j) {
@@ -220,12 +223,14 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_wait(&p_ready[t], (uint32_t)(j & 1));
             tc_fence_after();
 #ifdef EA_ATTN_TIMING
-            const bool md = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 8 && j < 16;
+            const bool md = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 8 && j < 16 && lane == 0;
             if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 0] = clock64();
 #endif
-            issue_PV(t, stage, (uint32_t)(t * 128), (uint32_t)(256 + t * 128), j == 0);
-            umma_commit(&pv_done[t]);
-            if (t == 1) umma_commit(&kv_empty[stage]);
+            // S_t(j+1) below is queued behind PV_t(j), so "S ready" already implies "PV retired":
+            // pv_done is only needed once, for the epilogue
+            EA_ISSUE(issue_PV(t, stage, (uint32_t)(t * 128), (uint32_t)(256 + t * 128), j == 0);
+                     if (!more) umma_commit(&pv_done[t]);
+                     if (t == 1) umma_commit(&kv_empty[stage]));
 #ifdef EA_ATTN_TIMING
             if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 1] = clock64();
 #endif
@@ -234,8 +239,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_wait(&kv_full[nstage], nphase);
                 tc_fence_after();
               }
-              issue_S(t, nstage, (uint32_t)(t * 128));
-              umma_commit(&s_full[t]);
+              EA_ISSUE(issue_S(t, nstage, (uint32_t)(t * 128)); umma_commit(&s_full[t]));
             }
 #ifdef EA_ATTN_TIMING
             if (md) ea_attn_dbg_mma[(t * 8 + j - 8) * 4 + 2] = clock64();
@@ -247,8 +251,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       } else {
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        issue_S(0, 0, 0);
-        umma_commit(&s_full[0]);
+        EA_ISSUE(issue_S(0, 0, 0); umma_commit(&s_full[0]));
         int stage = 0;
         uint32_t phase = 0;
         for (int j = 0; j < n_tiles; ++j) {
@@ -260,19 +263,16 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (more && p.stages > 1) {  // next logits tile while this one is in softmax
             mbar_wait(&kv_full[nstage], nphase);
             tc_fence_after();
-            issue_S(0, nstage, nbuf);
-            umma_commit(&s_full[(j + 1) & 1]);
+            EA_ISSUE(issue_S(0, nstage, nbuf); umma_commit(&s_full[(j + 1) & 1]));
           }
           mbar_wait(&p_ready[0], (uint32_t)(j & 1));
           tc_fence_after();
-          issue_PV(0, stage, (uint32_t)(j & 1) * 128u, 256u, j == 0);
-          umma_commit(&pv_done[0]);
-          umma_commit(&kv_empty[stage]);
+          EA_ISSUE(issue_PV(0, stage, (uint32_t)(j & 1) * 128u, 256u, j == 0); umma_commit(&pv_done[0]);
+                   umma_commit(&kv_empty[stage]));
           if (more && p.stages == 1) {
             mbar_wait(&kv_full[nstage], nphase);
             tc_fence_after();
-            issue_S(0, nstage, nbuf);
-            umma_commit(&s_full[(j + 1) & 1]);
+            EA_ISSUE(issue_S(0, nstage, nbuf); umma_commit(&s_full[(j + 1) & 1]));
           }
           stage = nstage;
           phase = nphase;
@@ -343,8 +343,8 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           l *= alpha;
         }
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
-          tc_fence_after();
+          if (NQT == 1) mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));  // O holds tiles 0..j-1
+          tc_fence_after();                // (NQT == 2: implied by s_full, see the MMA schedule)
 #pragma unroll 1
           for (int c = 0; c < p.dpad16; c += 16) {
             uint32_t o[16];
@@ -414,7 +414,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         l *= alpha;
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));
+        if (NQT == 1) mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < p.dpad16; c += 16) {
@@ -479,7 +479,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       EA_T(5);
     }
     // ---- epilogue: O / l
-    mbar_wait(&pv_done[t], (uint32_t)((n_tiles - 1) & 1));
+    mbar_wait(&pv_done[t], NQT == 2 ? 0u : (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
     const float inv_l = 1.f / l;
     ea_half* orow = p.out + (long long)b * p.o_bs + (long long)(row_ok ? q : 0) * p.o_ns +

@@ -721,7 +721,8 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
         if (t_chip > t_kb) t_kb = t_chip;
         if (t_lat > t_kb) t_kb = t_lat;
         double cost = (double)waves * (kbps * t_kb + 3500.0 + 8.0 * BN);
-        if (splits > 1) cost += 2500.0 + 2.0 * (BM * BN * 4.0) / 25.0;   // partial store + reduce
+        // partial store + barrier + distributed reduce (fitted to tools/exp_splitk.py, r01g)
+        if (splits > 1) cost += 3500.0 + 3.0 * (BM * BN * 4.0) / 25.0 + 150.0 * splits;
         if (cost < best.cost) best = {BN, st, splits, kbps, occ, cost, 0};
       }
     }

@@ -55,6 +55,7 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   long long lds;
   if (c < C1) { src = x + c; lds = ldx; } else { src = x2 + (c - C1); lds = ldx2; }
   if (active) {
+#pragma unroll 4
     for (int pp = p0 + pl; pp < p1; pp += lanes) {
       uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pp) * lds));
       if (cached) cache[(pp - p0) * nvec + v] = u;
@@ -558,7 +559,11 @@ __global__ void conv_smallcin_kernel(const ea_half* __restrict__ x, const float*
   pdl_wait();
   extern __shared__ float wsm[];  // [9*CIN][Cout] + bias[Cout]
   const int nw = 9 * CIN * Cout;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = w[i];
+  {  // filter bank -> shared memory, 16-byte loads, all issued before the first use (Cout % 8 == 0)
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float4* s4 = reinterpret_cast<float4*>(wsm);
+    for (int i = threadIdx.x; i < (nw >> 2); i += blockDim.x) s4[i] = __ldg(w4 + i);
+  }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[nw + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int ngrp = Cout >> 3;
@@ -776,7 +781,7 @@ extern "C" int ea_conv_in(const void* x, const float* w, const float* bias, void
   const int smem = (9 * Cin * Cout + Cout) * (int)sizeof(float);
   const long long total = (long long)B * H * W * (Cout / 8);
   int grid = (int)((total + 255) / 256);
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148) grid = 148;   // the 46 KB filter bank is loaded once per CTA: one CTA per SM
   if (grid < 1) grid = 1;
   cudaStream_t st = EA_STREAM(stream);
   const ea_half* xx = reinterpret_cast<const ea_half*>(x);
