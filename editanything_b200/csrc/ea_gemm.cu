@@ -64,6 +64,7 @@ struct GemmKParams {
   // split-K: blockIdx.z = split index; partial tiles go through `ws`, arrival counters in `cnt`
   int splits;
   int kb_per_split;
+  int no_spin;       // split-K without the sibling wait (concurrent streams)
   int pair_release;  // stages are released to the producer two at a time (even stage count >= 4)
   float* ws;   // [tiles][splits][128][BN] fp32
   int* cnt;    // [tiles][2]: arrived, done (zero between launches)
@@ -265,6 +266,8 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* cb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) &
+                                       ~uintptr_t(15));   // [2][256] bias + time-emb row vector
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -438,15 +441,107 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int r = wq * 32 + lane;        // tile row owned by this thread
     const int et = threadIdx.x;          // 0..127 among the epilogue threads
     RowInfo ri = row_info(p, tm, r);
+    const int ncol0 = tn * p.BN;
+    const bool geglu = p.act == EA_ACT_GEGLU;
+    const int half_bn = p.BN >> 1;
+    // Fast path (the common case): while the main loop runs, these otherwise idle warps stage
+    // bias (+ the per-image time-embedding row vector) for the tile's columns in shared memory and
+    // pull the first residual chunk into registers, so that after the accumulator is complete the
+    // per-chunk work is TMEM load -> FMA -> 16-byte stores with the NEXT chunk's residual already in
+    // flight (before: four dependent global round trips per 32-column chunk, ~5400 clk per tile).
+    const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
+    const bool fast = p.splits == 1 && !geglu && !p.out_f32 && !p.accumulate && (b_last - b_first) <= 1;
+    uint4 rnext[4];
+    const ea_half* res_row = nullptr;
+    if (fast) {
+      for (int i = et; i < p.BN; i += 128) {
+        const int col = ncol0 + i;
+        float v0 = 0.f, v1 = 0.f;
+        if (col < p.N) {
+          const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
+          v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
+          v1 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
+        }
+        cb[i] = v0;
+        cb[256 + i] = v1;
+      }
+      if (p.residual && ri.ok) {
+        res_row = p.residual + ri.m * p.ldr + ncol0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          rnext[q] = (ncol0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q)
+                                           : make_uint4(0, 0, 0, 0);
+      }
+      epi_bar_sync();
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #ifdef EA_GEMM_TIMING
     if (threadIdx.x == 0) EA_GT1(6);
 #endif
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const int ncol0 = tn * p.BN;
-    const bool geglu = p.act == EA_ACT_GEGLU;
-    const int half_bn = p.BN >> 1;
+    if (fast) {
+      const float* cbr = cb + (ri.batch != b_first ? 256 : 0);
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        uint4 rcur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+        const int n_first = ncol0 + c;
+        if (res_row && c + 32 < p.BN) {  // next chunk's residual: in flight during this chunk
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            rnext[q] = (n_first + 32 + q * 8 < p.N)
+                           ? __ldg(reinterpret_cast<const uint4*>(res_row + c + 32) + q)
+                           : make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
+        if (ri.ok && n_first < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (p.act == EA_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          } else if (p.act == EA_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+          }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+          }
+          if (res_row) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 a = ea_unpack2(rcur[q].x), b = ea_unpack2(rcur[q].y), cc = ea_unpack2(rcur[q].z),
+                     d = ea_unpack2(rcur[q].w);
+              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+              f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ri.m * p.ldo + n_first);
+          uint4* dst2 = p.out2 ? reinterpret_cast<uint4*>(p.out2 + ri.m * p.ldo2 + n_first) : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n_first + q * 8 < p.N) {
+              const uint4 o = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                         ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
+              dst[q] = o;
+              if (dst2) dst2[q] = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    } else
     if (p.splits == 1) {
       if (geglu) {
         // tile columns: [0, BN/2) = value half, [BN/2, BN) = gate half (weights pre-interleaved)
@@ -492,20 +587,29 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       __threadfence();
       epi_bar_sync();
       int* cnt = p.cnt + 2 * tile_id;
-      if (et == 0) {
-        atomicAdd(cnt, 1);
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(cnt) < p.splits) {
-          __nanosleep(40);
-          if (++spins > (1u << 24)) { asm volatile("trap;"); }
+      bool take_all = false;   // no_spin: the LAST split CTA to arrive finishes the whole tile
+      if (p.no_spin) {
+        if (et == 0) *reinterpret_cast<volatile int*>(cb) = atomicAdd(cnt, 1);
+        epi_bar_sync();
+        take_all = *reinterpret_cast<volatile int*>(cb) == p.splits - 1;
+        epi_bar_sync();
+      } else {
+        if (et == 0) {
+          atomicAdd(cnt, 1);
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(cnt) < p.splits) {
+            __nanosleep(40);
+            if (++spins > (1u << 24)) { asm volatile("trap;"); }
+          }
         }
+        epi_bar_sync();
       }
-      epi_bar_sync();
       __threadfence();
+      if (!p.no_spin || take_all) {
       const int chunks = geglu ? (half_bn >> 5) : (p.BN >> 5);
       const int units = BM * chunks;
-      const int u0 = (int)(((long long)units * blockIdx.z) / p.splits);
-      const int u1 = (int)(((long long)units * (blockIdx.z + 1)) / p.splits);
+      const int u0 = take_all ? 0 : (int)(((long long)units * blockIdx.z) / p.splits);
+      const int u1 = take_all ? units : (int)(((long long)units * (blockIdx.z + 1)) / p.splits);
       // Stage 1 (all 128 threads, float4 granularity, loads of the sibling partials unrolled for
       // memory-level parallelism) sums this CTA's share into the now-idle pipeline smem; stage 2
       // runs the fused epilogue on whole 32-column units.  Pieces of <= 64 units (<= 17 KB).
@@ -571,12 +675,17 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       epi_bar_sync();
       if (et == 0) {
-        int old = atomicAdd(cnt + 1, 1);
-        if (old == p.splits - 1) {  // last finisher: re-arm the counters for the next launch
+        if (take_all) {
           cnt[0] = 0;
-          cnt[1] = 0;
+        } else {
+          int old = atomicAdd(cnt + 1, 1);
+          if (old == p.splits - 1) {  // last finisher: re-arm the counters for the next launch
+            cnt[0] = 0;
+            cnt[1] = 0;
+          }
         }
       }
+      }  // !no_spin || take_all
     }
   }
 
@@ -887,6 +996,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   const int n_tiles = (a->N + p.BN - 1) / p.BN;
   p.splits = plan.splits;
   p.kb_per_split = plan.kbps;
+  p.no_spin = a->no_spin;
   if (p.splits > 1) {
     const long long tiles = (long long)m_tiles * n_tiles;
     if (!ws_floats || tiles > 8192 || tiles * p.splits * (long long)(BM * p.BN) > ws_floats ||
@@ -908,7 +1018,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   if (stages >= 5 && (stages & 1) && a->force_stages == 0) --stages;   // even: stages are released in pairs
   p.stages = stages;
   p.pair_release = (stages >= 4 && stages % 2 == 0) ? 1 : 0;
-  const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * 256 * 4 + 1024;
   static int max_set[2] = {0, 0};
   if (smem_bytes > max_set[two]) {
     cudaError_t se = two ? cudaFuncSetAttribute(ea_gemm_kernel<true>,

@@ -26,12 +26,14 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
                 const ea_half* __restrict__ x2, long long ldx2,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 ea_half* __restrict__ out, long long ldo, int HW, int C, int groups, float eps,
-                int silu, int chunks, int ppc, int cached, float* __restrict__ ws) {
+                int silu, int chunks, int ppc, int cached, int part_bytes, int phase,
+                float* __restrict__ ws) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   float* sh = reinterpret_cast<float*>(gn_smem);                  // [2*groups]
-  uint4* cache = reinterpret_cast<uint4*>(gn_smem + 512);        // [ppc][nvec] (if cached)
+  float* part = reinterpret_cast<float*>(gn_smem + 512);          // [lanes][2][C] per-lane partials
+  uint4* cache = reinterpret_cast<uint4*>(gn_smem + 512 + part_bytes);  // [ppc][nvec] (if cached)
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * ppc;
   const int p1 = min(HW, p0 + ppc);
@@ -44,16 +46,20 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   const int c = v << 3;
   float* wsb = ws + (long long)b * (2 * groups + 2);
   int* cnt = reinterpret_cast<int*>(wsb + 2 * groups);
+  // phase 0: fused (pass 1, image-wide spin barrier, pass 2).  phases 1 / 2: the two passes as
+  // SEPARATE launches without any inter-CTA wait - used when several streams run concurrently and
+  // a spinning, partially resident grid could starve another one (no co-residency guarantee then).
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
+  const ea_half* src;
+  long long lds;
+  if (c < C1) { src = x + c; lds = ldx; } else { src = x2 + (c - C1); lds = ldx2; }
+  if (phase != 2) {
   // ---- pass 1: load (cache) + per-thread, per-channel partial sums (the thread's 8 channels
   //      are fixed, so their groups are too: shared-memory atomics only once, after the loop)
   float cs[8], cq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  const ea_half* src;
-  long long lds;
-  if (c < C1) { src = x + c; lds = ldx; } else { src = x2 + (c - C1); lds = ldx2; }
   if (active) {
 #pragma unroll 4
     for (int pp = p0 + pl; pp < p1; pp += lanes) {
@@ -64,26 +70,29 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
 #pragma unroll
       for (int j = 0; j < 8; ++j) { cs[j] += vals[j]; cq[j] += vals[j] * vals[j]; }
     }
-    // combine channels of the same group before touching shared memory
-    int gprev = c / cpg;
-    float s = 0.f, q = 0.f;
+    // per-(pixel lane, channel) partials -> shared memory (no atomics: 480 threads x 16 contended
+    // shared atomics used to cost ~4 us per launch)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      if (g != gprev) {
-        atomicAdd(&sh[gprev * 2], s);
-        atomicAdd(&sh[gprev * 2 + 1], q);
-        s = 0.f; q = 0.f; gprev = g;
-      }
-      s += cs[j]; q += cq[j];
+      part[(pl * 2 + 0) * C + c + j] = cs[j];
+      part[(pl * 2 + 1) * C + c + j] = cq[j];
     }
-    atomicAdd(&sh[gprev * 2], s);
-    atomicAdd(&sh[gprev * 2 + 1], q);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups * 2) {   // one thread per (group, sum | sumsq): lanes x cpg adds
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float* pp = part + (l * 2 + which) * C + g * cpg;
+      for (int j = 0; j < cpg; ++j) acc += pp[j];
+    }
+    sh[threadIdx.x] = acc;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&wsb[i], sh[i]);
   __threadfence();
   __syncthreads();
+  if (phase == 1) return;
   // ---- image-wide barrier
   if (threadIdx.x == 0) {
     atomicAdd(cnt, 1);
@@ -95,6 +104,7 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   }
   __syncthreads();
   __threadfence();
+  }  // phase != 2
   // ---- pass 2: y = x * a + b with a = rstd*gamma, b = beta - mean*a (per channel of this thread)
   if (active) {
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
@@ -646,8 +656,9 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
   threads = ((threads + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   const long long cache_bytes = (long long)ppc * nvec * 16;
-  const int cached = cache_bytes <= 200 * 1024;
-  const int smem = 512 + (cached ? (int)cache_bytes : 0);
+  const int part_bytes = ((threads / nvec) * 2 * a->C * 4 + 15) & ~15;
+  const int cached = cache_bytes + part_bytes <= 200 * 1024;
+  const int smem = 512 + part_bytes + (cached ? (int)cache_bytes : 0);
   static int max_set = 0;
   if (smem > max_set) {
     if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -656,9 +667,19 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
     max_set = smem;
   }
   dim3 grid(chunks, a->B);
+  if (a->two_pass) {
+    const int smem1 = 512 + part_bytes;
+    for (int phase = 1; phase <= 2; ++phase)
+      ea_launch(gn_fused_kernel, grid, dim3(threads), (size_t)smem1, st,
+                reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
+                a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
+                a->groups, a->eps, a->silu, chunks, ppc, 0, part_bytes, phase, a->workspace);
+    ea_count_launch();
+    return EA_LAUNCH_OK();
+  }
   ea_launch(gn_fused_kernel, dim3(grid), dim3(threads), (size_t)(smem), st, reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
       a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
-      a->groups, a->eps, a->silu, chunks, ppc, cached, a->workspace);
+      a->groups, a->eps, a->silu, chunks, ppc, cached, part_bytes, 0, a->workspace);
   return EA_LAUNCH_OK();
 }
 

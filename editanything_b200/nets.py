@@ -291,8 +291,20 @@ class UNetRunner:
         self.unet, self.cns, self.dev = unet, list(controlnets), device
         self.ops = unet.ops
         self.hdt = unet.hdt
+        import os
+        self.concurrent = os.environ.get("EA_CONCURRENT", "1") != "0"
+        self._streams = []
+        self._lane_gn = {}
 
-    def _encoder(self, net: PackedNet, x_half, emb_all, ctxc, gn_ws, guided_hint=None, sinks=None, scale=1.0):
+    def _lane_ws(self, B, n):
+        """One zeroed GroupNorm workspace per concurrent stream."""
+        key = (B, n)
+        if key not in self._lane_gn:
+            self._lane_gn[key] = [torch.zeros(B * (32 * 2 + 2), device=self.dev, dtype=torch.float32) for _ in range(n)]
+        return self._lane_gn[key]
+
+    def _encoder(self, net: PackedNet, x_half, emb_all, ctxc, gn_ws, guided_hint=None, sinks=None, scale=1.0,
+                 deferred=None):
         """Runs input_blocks + middle.  For the UNet (`sinks` is a dict of concat slots) each skip is
         dual-stored into its decoder concat slot; for a ControlNet each zero-conv accumulates
         `scale * zero_conv(h)` into the slot instead of materialising the residual."""
@@ -321,8 +333,12 @@ class UNetRunner:
                 c = h.shape[-1]
                 M = h.shape[0] * h.shape[1] * h.shape[2]
                 p = f"zero_convs.{i}.0"
-                o.gemm(h.view(M, c), w[p + ".w"], slot, M=M, bias=w[p + ".b"], out_scale=scale, accumulate=True,
-                       ldo=slot.stride(2))
+                if deferred is not None:   # run after the concurrent streams have joined (shared slots)
+                    deferred.append((h.view(M, c), w[p + ".w"], slot, dict(M=M, bias=w[p + ".b"], out_scale=scale,
+                                                                        accumulate=True, ldo=slot.stride(2))))
+                else:
+                    o.gemm(h.view(M, c), w[p + ".w"], slot, M=M, bias=w[p + ".b"], out_scale=scale, accumulate=True,
+                           ldo=slot.stride(2))
         mid_sink = sinks["mid"]
         if is_unet:
             h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws, final_out=mid_sink)
@@ -330,8 +346,12 @@ class UNetRunner:
             h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws)
             c = h.shape[-1]
             M = h.shape[0] * h.shape[1] * h.shape[2]
-            o.gemm(h.view(M, c), w["mid_out.w"], mid_sink, M=M, bias=w["mid_out.b"], out_scale=scale,
-                   accumulate=True, ldo=mid_sink.stride(2))
+            if deferred is not None:
+                deferred.append((h.view(M, c), w["mid_out.w"], mid_sink, dict(M=M, bias=w["mid_out.b"], out_scale=scale,
+                                                                             accumulate=True, ldo=mid_sink.stride(2))))
+            else:
+                o.gemm(h.view(M, c), w["mid_out.w"], mid_sink, M=M, bias=w["mid_out.b"], out_scale=scale,
+                       accumulate=True, ldo=mid_sink.stride(2))
         return h
 
     def alloc_sinks(self, B, H, W_):
@@ -375,11 +395,38 @@ class UNetRunner:
         if embs is None:
             embs = self.compute_embs(t_dev, B)
         emb_u = embs[0]
-        self._encoder(un, x_half, emb_u, ctx_cache[0], gn_ws, sinks=sinks)
-        for k, cn in enumerate(self.cns):
-            emb_c = embs[1 + k]
-            self._encoder(cn, x_half, emb_c, ctx_cache[1 + k], gn_ws, guided_hint=hints[k], sinks=sinks,
-                          scale=float(scales[k]))
+        concurrent = self.concurrent and len(self.cns) > 0 and hasattr(o, "set_lane") and x_half.is_cuda
+        if concurrent:
+            # The UNet encoder and every ControlNet only READ x and write their own activations: run
+            # them on parallel streams (many of their launches cannot fill 148 SMs on their own), join,
+            # then apply the zero-conv accumulations into the shared skip slots on the main stream.
+            # Inside the concurrent region GroupNorm / split-K use their variants without inter-CTA
+            # waits, and each stream has its own scratch lane.
+            main = torch.cuda.current_stream()
+            if len(self._streams) < len(self.cns):
+                self._streams = [torch.cuda.Stream() for _ in self.cns]
+            lanes_ws = self._lane_ws(B, len(self.cns) + 1)
+            deferred = []
+            for s in self._streams:
+                s.wait_stream(main)
+            o.set_lane(0, True)
+            self._encoder(un, x_half, emb_u, ctx_cache[0], lanes_ws[0], sinks=sinks)
+            for k, cn in enumerate(self.cns):
+                with torch.cuda.stream(self._streams[k]):
+                    o.set_lane(1 + k, True)
+                    self._encoder(cn, x_half, embs[1 + k], ctx_cache[1 + k], lanes_ws[1 + k], guided_hint=hints[k],
+                                  sinks=sinks, scale=float(scales[k]), deferred=deferred)
+            for s in self._streams:
+                main.wait_stream(s)
+            o.set_lane(0, False)
+            for a_, w_, out_, kw_ in deferred:
+                o.gemm(a_, w_, out_, **kw_)
+        else:
+            self._encoder(un, x_half, emb_u, ctx_cache[0], gn_ws, sinks=sinks)
+            for k, cn in enumerate(self.cns):
+                emb_c = embs[1 + k]
+                self._encoder(cn, x_half, emb_c, ctx_cache[1 + k], gn_ws, guided_hint=hints[k], sinks=sinks,
+                              scale=float(scales[k]))
         topo = un.topo
         cats = sinks["cats"]
         h = None

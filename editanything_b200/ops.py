@@ -34,12 +34,22 @@ def reset_launch_count():
 
 _GEMM_WS = {}
 GEMM_WS_BYTES = 65536 + 48 * 1024 * 1024
+_LANE = [0]          # workspace lane: kernels on concurrently running streams must not share scratch
+_CONCURRENT = [False]
+
+
+def set_lane(lane, concurrent):
+    """Select the scratch lane of the calling stream and whether other streams run concurrently
+    (then GroupNorm and split-K GEMMs use their variants without inter-CTA waits)."""
+    _LANE[0] = lane
+    _CONCURRENT[0] = bool(concurrent)
 
 
 def gemm_workspace(device):
-    """Per-device split-K scratch of ea_gemm (64 KB zeroed counters + fp32 partial tiles); shared by
-    every GEMM on the stream, allocated once so CUDA-graph captures see a stable address."""
-    key = (device.type, device.index)
+    """Per-device (and per concurrent lane) split-K scratch of ea_gemm (64 KB zeroed counters + fp32
+    partial tiles); shared by every GEMM on a stream, allocated once so CUDA-graph captures see a
+    stable address."""
+    key = (device.type, device.index, _LANE[0])
     ws = _GEMM_WS.get(key)
     if ws is None:
         ws = torch.zeros(GEMM_WS_BYTES, device=device, dtype=torch.uint8)
@@ -100,6 +110,7 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     g.force_stages = force_stages
     g.force_splits = force_splits
     g.force_2cta = force_2cta
+    g.no_spin = 1 if _CONCURRENT[0] else 0
     ws = gemm_workspace(a.device)
     g.workspace = ws.data_ptr()
     g.workspace_bytes = ws.numel()
@@ -140,6 +151,7 @@ def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True,
     g.ldo = ldo if ldo is not None else C_
     g.B, g.HW, g.C, g.groups = B, HW, C_, groups
     g.eps, g.silu = eps, 1 if silu else 0
+    g.two_pass = 1 if _CONCURRENT[0] else 0
     if workspace is None:
         workspace = torch.zeros(B * (groups * 2 + 2), device=x.device, dtype=torch.float32)
     g.workspace = workspace.data_ptr()

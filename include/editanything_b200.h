@@ -104,6 +104,8 @@ typedef struct ea_gemm_args {
   int force_stages;          /* 0 = auto */
   int force_splits;          /* 0 = auto; 1 = never split K; n = split K n ways (testing) */
   int force_2cta;            /* 0 = auto; 1 = CTA pairs (tcgen05 cta_group::2, M = 256); -1 = never */
+  int no_spin;               /* 1: split-K without the sibling wait - the last split CTA to arrive reduces
+                                the whole tile (required when other streams run kernels concurrently) */
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K
@@ -147,6 +149,8 @@ typedef struct ea_gn_args {
   void* out; long long ldo;
   int B, HW, C, groups;
   float eps; int silu;
+  int two_pass;              /* 1: statistics and normalisation as two launches with no inter-CTA wait
+                                (required when other streams run kernels concurrently) */
   float* workspace;          /* >= B*(2*groups+2) floats, ZERO before the first call (the kernel
                                 leaves it zero); one workspace may serve every call on a stream */
 } ea_gn_args;
