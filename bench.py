@@ -185,7 +185,7 @@ def run_ours(args, rank, world, local_rank):
     finite = bool(torch.isfinite(eng.latents()).all().item())
 
     # ---- SAM ViT-H encoder (once per image) -----------------------------------------------------
-    sam_ms, sam_note = None, "not built yet: images/s below is denoise-only"
+    sam_ms, sam_note, sam = None, "skipped (--no-sam): images/s below is denoise-only", None
     try:
         if args.no_sam:
             raise ImportError("skipped")
@@ -242,32 +242,50 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e: host buffers in, host result out, through the public engine API ---------------------
     e2e = None
     if (rank == 0 or world > 1) and not args.no_e2e:
+        # One image end to end through the public engine API, inputs in PINNED HOST memory:
+        #   H2D preprocessed image -> SAM ViT-H encode -> D2H embedding (what the mask decoder / AMG consume)
+        #   H2D prompt embeddings, ControlNet conditioning images, initial noise -> prepare (ctx K/V, hint
+        #   stacks) -> 50 fused steps -> D2H latents.
+        # One untimed warm-up image (CUDA-graph capture, allocator), then n_img timed images.
         hx, hctx = x[:1].pin_memory(), ctx.pin_memory()
         hh = [h.pin_memory() for h in hints]
-        n_img = 2
+        himg = torch.randn(1, 3, 1024, 1024).pin_memory() if sam is not None else None
+        n_img = 3
+
+        def one_image():
+            emb = None
+            if sam is not None:
+                emb = sam.encode(himg.to(dev, non_blocking=True)).cpu()
+            eng.prepare(hctx.to(dev, non_blocking=True), [h.to(dev, non_blocking=True) for h in hh], [0.5, 1.0])
+            eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
+            for i in range(DDIM_STEPS):
+                eng.step(int(ts[i]), float(a[i]), float(ap[i]))
+            return eng.latents().cpu(), emb
+
+        one_image()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(n_img):
-            eng.prepare(hctx.to(dev, non_blocking=True), [h.to(dev, non_blocking=True) for h in hh], [0.5, 1.0])
-            eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
-            for i in range(DDIM_STEPS):
-                eng.step(int(ts[i]), float(a[i]), float(ap[i]))
-            res = eng.latents().cpu()
+            res, emb = one_image()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
+            from editanything_b200.sharding import gather_sharded
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
-            gathered = [torch.empty_like(res).to(dev) for _ in range(world)]
-            dist.all_gather(gathered, res.to(dev))   # the single end-of-job collective
-        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh)) * 4
+            allres = gather_sharded(res.to(dev), world, rank, world)   # the single end-of-job collective
+            assert allres.shape[0] == world
+        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh) + (himg.numel() if himg is not None else 0)) * 4
+        d2h = (res.numel() + (emb.numel() if emb is not None else 0)) * 4
         e2e = {"value": round(world * n_img / dt, 4), "unit": "images/s",
-               "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": res.numel() * 4 // DDIM_STEPS,
-               "note": "engine API: pinned host ctx/hints/latents -> H2D -> prepare (ctx K/V, hint stack) -> 50 fused "
-                       "steps -> D2H latents; SAM/VAE not included"}
+               "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": d2h // DDIM_STEPS,
+               "ms_per_image": round(dt / n_img * 1e3, 2), "images_timed": n_img,
+               "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host ctx / hints / "
+                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> D2H latents; 1 untimed warm-up "
+                       "image; VAE / text encoder / mask decoder not included (out of scope, SURVEY.md 8f)"}
 
     line = {
         "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",

@@ -106,6 +106,11 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   __threadfence();
   }  // phase != 2
   // ---- pass 2: y = x * a + b with a = rstd*gamma, b = beta - mean*a (per channel of this thread)
+  // the image's 2*groups statistics come back in ONE L2 round trip (per-thread dependent loads of
+  // "its" groups cost several serialized round trips: profiles/r01j_gn_ncu_full.txt)
+  __syncthreads();
+  if (threadIdx.x < groups * 2) sh[threadIdx.x] = __ldcg(&wsb[threadIdx.x]);
+  __syncthreads();
   if (active) {
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
     float av[8], bv[8];
@@ -122,7 +127,7 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
       for (int j = 0; j < 8; ++j) {
         const int g = (c + j) / cpg;
         if (g != gprev) {
-          const float s = __ldcg(&wsb[g * 2]), q = __ldcg(&wsb[g * 2 + 1]);
+          const float s = sh[g * 2], q = sh[g * 2 + 1];
           mean = s * inv_n;
           rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
           gprev = g;
