@@ -38,6 +38,7 @@ struct AttnKParams {
   int dpad16;  // d rounded up to 16: MMA N of the PV product
   int stages;
   int p_smem;  // 1: stage P through shared memory (SS MMA) instead of TMEM (testing fallback)
+  int bias_bytes;  // shared memory for the rel_w rows of the CTA's queries (BIAS kernels), 16-byte multiple
   int dbg_skip;  // experiment builds: bit0 = skip the PV MMAs, bit1 = skip the S MMAs, bit2 = V K-major view
   float scale_log2;
   ea_half* out;
@@ -82,7 +83,8 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sKV = sQ + NQT * p.nd * AT_ATOM;
   const int kv_stage_bytes = 2 * p.nd * AT_ATOM;
   uint8_t* sP = sKV + p.stages * kv_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (p.p_smem ? NQT * 2 * AT_ATOM : 0));
+  float* rw_s = reinterpret_cast<float*>(sP + (p.p_smem ? NQT * 2 * AT_ATOM : 0));   // [NQT*128][rel_s+1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rw_s) + p.bias_bytes);
   uint64_t* q_full = bars;                      // [1]
   uint64_t* kv_full = bars + 1;                 // [AT_MAX_STAGES]
   uint64_t* kv_empty = kv_full + AT_MAX_STAGES; // [AT_MAX_STAGES]
@@ -290,11 +292,12 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tmem_O = tmem_base + lane_off + (NQT == 2 ? (uint32_t)(256 + t * 128) : 256u);
     const float LOG2E = 1.4426950408889634f;
     const float* rh = nullptr;
-    const float* rw = nullptr;
     if (BIAS) {
       const long long bh = (long long)b * p.heads + head;
       rh = p.rel_h + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s;
-      rw = p.rel_w + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s;
+      const float* rw = p.rel_w + (bh * p.Nq + (row_ok ? q : 0)) * p.rel_s;
+      float* dst = rw_s + (t * AT_BQ + r) * (p.rel_s + 1);
+      for (int i = 0; i < p.rel_s; ++i) dst[i] = row_ok ? __ldg(rw + i) * LOG2E : 0.f;   // own row only
     }
     float m_run = -INFINITY;  // running max in the scaled log2 domain
     float l = 0.f;
@@ -310,7 +313,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       EA_T(1);
       const uint32_t tmem_S = tmem_base + lane_off + (uint32_t)sb * 128u;
       const int valid = min(AT_BKV, p.Nkv - j * AT_BKV);  // keys of this tile that exist (>= 1)
-      if (!BIAS) {
+      {
         // ---- whole 128-column logits row in registers: ONE TMEM round trip per tile
         uint32_t v[4][32];
         tmem_ld32(tmem_S, v[0]);
@@ -319,6 +322,35 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld32(tmem_S + 96u, v[3]);
         tmem_ld_wait();
         EA_T(2);
+        if (BIAS) {
+          // t = s*scale*log2e + (rel_h[q, kh] + rel_w[q, kw])*log2e, written back over v.  rel_w's row
+          // (pre-multiplied by log2e) sits in shared memory, rel_h comes through L1 (2 values/tile
+          // for the 64x64 global grid).
+          const float* rwr = rw_s + (t * AT_BQ + r) * (p.rel_s + 1);
+          const int kk0 = j * AT_BKV;
+          int kh = kk0 / p.rel_s, kw = kk0 - kh * p.rel_s;
+          if ((p.rel_s & 31) == 0) {      // a 32-column chunk never crosses a key row: no branches
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                v[h][i] = __float_as_uint(fmaf(__uint_as_float(v[h][i]), p.scale_log2, rwr[kw + i] + bh_));
+              kw += 32;
+              if (kw == p.rel_s) { kw = 0; ++kh; }
+            }
+          } else {
+            float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                v[h][i] = __float_as_uint(fmaf(__uint_as_float(v[h][i]), p.scale_log2, rwr[kw] + bh_));
+                if (++kw == p.rel_s) { kw = 0; ++kh; bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E; }
+              }
+            }
+          }
+        }
         if (valid < AT_BKV) {  // last, partial K/V tile: keys that do not exist get -inf
 #pragma unroll
           for (int h = 0; h < 4; ++h)
@@ -334,7 +366,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mx2 = fmaxf(mx2, __uint_as_float(v[2][i]));
           mx3 = fmaxf(mx3, __uint_as_float(v[3][i]));
         }
-        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // scale > 0
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * (BIAS ? 1.f : p.scale_log2);  // scale > 0
         float alpha = 1.f;
         const bool need = m_tile > m_run + 8.f;
         if (need) {
@@ -364,10 +396,11 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(v[h][i]), p.scale_log2, neg_m));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(v[h][i + 1]), p.scale_log2, neg_m));
-            const float e2 = ex2_approx(fmaf(__uint_as_float(v[h][i + 2]), p.scale_log2, neg_m));
-            const float e3 = ex2_approx(fmaf(__uint_as_float(v[h][i + 3]), p.scale_log2, neg_m));
+            const float sc = BIAS ? 1.f : p.scale_log2;   // BIAS: v already holds the scaled logits
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[h][i]), sc, neg_m));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[h][i + 1]), sc, neg_m));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(v[h][i + 2]), sc, neg_m));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(v[h][i + 3]), sc, neg_m));
             s0 += e0; s1 += e1; s2 += e2; s3 += e3;
             pk[i >> 1] = ea_pack2(e0, e1);
             pk[(i >> 1) + 1] = ea_pack2(e2, e3);
@@ -386,91 +419,7 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         l += (s0 + s1) + (s2 + s3);
-      } else {
-      // ---- BIAS (SAM rel-pos) path: two passes over TMEM, bias terms fetched per element
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < AT_BKV; c += 32) {
-        if (c >= valid) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_S + (uint32_t)c, v);
-        tmem_ld_wait();
-        int kk = j * AT_BKV + c;
-        int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
-        float bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float tt = fmaf(__uint_as_float(v[i]), p.scale_log2, fmaf(__ldg(rw + kw), LOG2E, bh_));
-          if (c + i < valid) mx = fmaxf(mx, tt);
-          if (++kw == p.rel_s) { kw = 0; ++kh; bh_ = __ldg(rh + min(kh, p.rel_s - 1)) * LOG2E; }
-        }
       }
-      const float m_tile = mx;
-      float alpha = 1.f;
-      const bool need = m_tile > m_run + 8.f;
-      if (need) {
-        alpha = ex2_approx(m_run - m_tile);
-        m_run = m_tile;
-        l *= alpha;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        if (NQT == 1) mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < p.dpad16; c += 16) {
-          uint32_t o[16];
-          tmem_ld16(tmem_O + (uint32_t)c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tmem_O + (uint32_t)c, o);
-        }
-        tmem_st_wait();
-      }
-      const float neg_m = -m_run;
-#pragma unroll 1
-      for (int c = 0; c < AT_BKV; c += 32) {
-        uint32_t pk[16];
-        if (c < valid) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + (uint32_t)c, v);
-          tmem_ld_wait();
-          float e[32];
-          int kk = j * AT_BKV + c;
-          int kh = kk / p.rel_s, kw = kk - kh * p.rel_s;
-          float bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float tt = fmaf(__uint_as_float(v[i]), p.scale_log2, fmaf(__ldg(rw + kw), LOG2E, bh_));
-            e[i] = (c + i < valid) ? ex2_approx(tt) : 0.f;
-            if (++kw == p.rel_s) {
-              kw = 0; ++kh;
-              bh_ = fmaf(__ldg(rh + min(kh, p.rel_s - 1)), LOG2E, neg_m);
-            }
-          }
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) { s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3]; }
-          l += (s0 + s1) + (s2 + s3);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = ea_pack2(e[2 * i], e[2 * i + 1]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        }
-        if (p.p_smem) {
-          uint8_t* prow = sP + (t * 2 + (c >> 6)) * AT_ATOM + r * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c16 = ((c & 63) >> 3) + g;
-            *reinterpret_cast<uint4*>(prow + ((c16 ^ (r & 7)) << 4)) =
-                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          }
-        } else {
-          tmem_st16(tmem_S + (uint32_t)(c >> 1), pk);
-        }
-      }
-      }  // BIAS
       EA_T(4);
       if (p.p_smem) fence_proxy_async();
       else tmem_st_wait();
@@ -592,12 +541,14 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   }
   if (force_nqt == 1 || force_nqt == 2) nqt = (force_nqt == 2 && p.dpad16 > 128) ? 1 : force_nqt;
   const int budget = 225 * 1024 - 1024 - 256;
-  const int fixed = nqt * p.nd * AT_ATOM + (p.p_smem ? nqt * 2 * AT_ATOM : 0);
+  const bool has_bias = a->rel_h != nullptr;
+  auto bias_bytes_for = [&](int n) { return has_bias ? ((n * AT_BQ * (a->rel_s + 1) * 4 + 15) & ~15) : 0; };
+  const int fixed = nqt * p.nd * AT_ATOM + (p.p_smem ? nqt * 2 * AT_ATOM : 0) + bias_bytes_for(nqt);
   int stages = (budget - fixed) / (2 * p.nd * AT_ATOM);
   if (stages > AT_MAX_STAGES) stages = AT_MAX_STAGES;
   if (nqt == 2 && stages < 2) {  // the ping-pong schedule needs two K/V stages
     nqt = 1;
-    const int fixed1 = p.nd * AT_ATOM + (p.p_smem ? 2 * AT_ATOM : 0);
+    const int fixed1 = p.nd * AT_ATOM + (p.p_smem ? 2 * AT_ATOM : 0) + bias_bytes_for(1);
     stages = (budget - fixed1) / (2 * p.nd * AT_ATOM);
     if (stages > AT_MAX_STAGES) stages = AT_MAX_STAGES;
   }
@@ -612,9 +563,10 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   if (encode_qkv(&tk, a->k, a->d, a->heads, a->Nkv, a->B, a->k_ns, a->k_bs)) return EA_ERR_TMAP;
   if (encode_qkv(&tv, a->v, a->d, a->heads, a->Nkv, a->B, a->v_ns, a->v_bs)) return EA_ERR_TMAP;
 
+  p.bias_bytes = bias_bytes_for(nqt);
   const int smem_bytes = nqt * p.nd * AT_ATOM + p.stages * 2 * p.nd * AT_ATOM +
-                         (p.p_smem ? nqt * 2 * AT_ATOM : 0) + (1 + 2 * AT_MAX_STAGES + 6) * 8 + 16 +
-                         1024;
+                         (p.p_smem ? nqt * 2 * AT_ATOM : 0) + p.bias_bytes +
+                         (1 + 2 * AT_MAX_STAGES + 6) * 8 + 16 + 1024;
   dim3 grid((unsigned)((a->Nq + AT_BQ * nqt - 1) / (AT_BQ * nqt)), (unsigned)a->heads,
             (unsigned)a->B);
   int st;

@@ -428,33 +428,44 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
 }
 
 // ------------------------------ SAM helpers --------------------------------
+// Decomposed relative-position terms (HF modeling_sam.py:789-801):
+//   rel_h[bh, (qh,qw), kh] = sum_c q[b,(qh,qw),h,c] * Rh[qh, kh, c]      (blockIdx.z = 0, CTA <-> fixed qh)
+//   rel_w[bh, (qh,qw), kw] = sum_c q[b,(qh,qw),h,c] * Rw[qw, kw, c]      (blockIdx.z = 1, CTA <-> fixed qw)
+// One CTA = one (fixed coordinate f, batch*head): the S query rows that share R[f] and the S x d
+// table slice live in shared memory (row stride d+1 floats: conflict-free), thread <-> output
+// column k, looping over the S rows (q[row][c] is a warp broadcast).
 __global__ void sam_relpos_kernel(const ea_half* __restrict__ q, long long q_bs, long long q_ns,
                                   const float* __restrict__ Rh, const float* __restrict__ Rw,
                                   float* __restrict__ rel_h, float* __restrict__ rel_w, int B,
                                   int heads, int S, int d) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = (long long)B * heads * S * S * 2 * S;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int kk = (int)(idx % (2 * S));
-    long long t = idx / (2 * S);
-    int qi = (int)(t % (S * S));
-    long long bh = t / (S * S);
-    int hd = (int)(bh % heads);
-    int b = (int)(bh / heads);
-    int qh = qi / S, qw = qi - qh * S;
-    const ea_half* qp = q + (long long)b * q_bs + (long long)qi * q_ns + (long long)hd * d;
-    const bool is_h = kk < S;
-    int k = is_h ? kk : kk - S;
-    const float* rp = is_h ? Rh + ((long long)qh * S + k) * d : Rw + ((long long)qw * S + k) * d;
+  extern __shared__ float rp_sm[];
+  const int f = blockIdx.x;              // fixed coordinate: qh (z = 0) or qw (z = 1)
+  const int bh = blockIdx.y;
+  const bool is_h = blockIdx.z == 0;
+  const int b = bh / heads, hd = bh - b * heads;
+  const int ld = d + 1;
+  float* qs = rp_sm;                     // [S][d+1]
+  float* rs = rp_sm + S * ld;            // [S][d+1]
+  const float* R = (is_h ? Rh : Rw) + (long long)f * S * d;
+  for (int i = threadIdx.x; i < S * d; i += blockDim.x) {
+    const int row = i / d, c = i - row * d;
+    rs[row * ld + c] = __ldg(R + i);
+    const int qi = is_h ? f * S + row : row * S + f;   // the S queries that share R[f]
+    qs[row * ld + c] = ea_h2f(q[(long long)b * q_bs + (long long)qi * q_ns + (long long)hd * d + c]);
+  }
+  __syncthreads();
+  float* dst = is_h ? rel_h : rel_w;
+  for (int o = threadIdx.x; o < S * S; o += blockDim.x) {
+    const int row = o / S, k = o - row * S;
+    const float* qr = qs + row * ld;
+    const float* rr = rs + k * ld;
     float acc = 0.f;
-    for (int c = 0; c < d; c += 2) {
-      float2 qv = ea_unpack2(*reinterpret_cast<const uint32_t*>(qp + c));
-      acc += qv.x * __ldg(rp + c) + qv.y * __ldg(rp + c + 1);
-    }
-    float* dst = is_h ? rel_h : rel_w;
-    dst[(bh * S * S + qi) * S + k] = acc;
+#pragma unroll 8
+    for (int c = 0; c < d; ++c) acc = fmaf(qr[c], rr[c], acc);
+    const int qi = is_h ? f * S + row : row * S + f;
+    dst[((long long)bh * S * S + qi) * S + k] = acc;
   }
 }
 
@@ -754,9 +765,20 @@ extern "C" int ea_sam_relpos(const void* q, long long q_bs, long long q_ns, cons
                              const float* Rw, float* rel_h, float* rel_w, int B, int heads, int S,
                              int d, void* stream) {
   if (!q || !Rh || !Rw || !rel_h || !rel_w) return EA_ERR_ARG;
-  if (d % 2 != 0) return EA_ERR_SHAPE;
-  long long total = (long long)B * heads * S * S * 2 * S;
-  ea_launch(sam_relpos_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), reinterpret_cast<const ea_half*>(q), q_bs, q_ns, Rh, Rw, rel_h, rel_w, B, heads, S, d);
+  if (d % 2 != 0 || S <= 0 || S > 128) return EA_ERR_SHAPE;
+  const int smem = 2 * S * (d + 1) * (int)sizeof(float);
+  if (smem > 200 * 1024) return EA_ERR_SHAPE;
+  static int max_set = 0;
+  if (smem > max_set) {
+    if (cudaFuncSetAttribute(sam_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return EA_ERR_CUDA;
+    max_set = smem;
+  }
+  dim3 grid((unsigned)S, (unsigned)(B * heads), 2);
+  int threads = S * S >= 1024 ? 256 : 128;
+  ea_launch(sam_relpos_kernel, grid, dim3(threads), (size_t)smem, EA_STREAM(stream),
+            reinterpret_cast<const ea_half*>(q), q_bs, q_ns, Rh, Rw, rel_h, rel_w, B, heads, S, d);
   return EA_LAUNCH_OK();
 }
 

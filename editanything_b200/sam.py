@@ -64,6 +64,7 @@ class SamEncoderEngine:
         w["neck3.g"], w["neck3.b"] = F(sd["neck.3.weight"]), F(sd["neck.3.bias"])
         self.w = w
         self._bufs = {}
+        self._graphs = {}
 
     def _half(self, t):
         return t.detach().to(device=self.dev, dtype=self.hdt).contiguous()
@@ -142,12 +143,38 @@ class SamEncoderEngine:
             x = self._block(i, x, B)
         return x
 
-    def encode(self, img):
-        """img: fp32 [B, 3, S, S] preprocessed (Sam.preprocess) -> fp32 [B, out_chans, S/16, S/16]."""
-        o, w, cfg = self.ops, self.w, self.cfg
+    def encode(self, img, use_graph=True):
+        """img: fp32 [B, 3, S, S] preprocessed (Sam.preprocess) -> fp32 [B, out_chans, S/16, S/16].
+        On the CUDA backend the ~320 launches of one encode are captured once per batch size into a
+        CUDA graph and replayed (the Python/ctypes launch path costs more than the kernels)."""
+        cfg = self.cfg
         B = img.shape[0]
         if tuple(img.shape[1:]) != (cfg.in_chans, cfg.img_size, cfg.img_size):
             raise ValueError(f"expected [B,{cfg.in_chans},{cfg.img_size},{cfg.img_size}], got {tuple(img.shape)}")
+        if not use_graph or self.ops is not _cuda_ops:
+            return self._encode_eager(img)
+        st = self._graphs.get(B)
+        if st is None:
+            static_in = torch.zeros(B, cfg.in_chans, cfg.img_size, cfg.img_size, device=self.dev, dtype=torch.float32)
+            static_in.copy_(img)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._encode_eager(static_in)          # warm-up: allocator, cudaFuncSetAttribute
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._encode_eager(static_in)
+            st = (g, static_in, static_out)
+            self._graphs[B] = st
+        g, static_in, static_out = st
+        static_in.copy_(img, non_blocking=True)
+        g.replay()
+        return static_out.clone()
+
+    def _encode_eager(self, img):
+        o, w, cfg = self.ops, self.w, self.cfg
+        B = img.shape[0]
         g, oc = cfg.grid, cfg.out_chans
         T = B * g * g
         x = self.tokens(img)
