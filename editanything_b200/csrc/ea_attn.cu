@@ -463,11 +463,273 @@ ea_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ea_attn_db_kernel: the long-sequence, small-head variant (d <= 64, no bias: the 64x64-latent
+// self-attention of SD1.5 with d = 40, 4096 - 16384 keys, where softmax's exp is the bound).
+// Same roles as ea_attn_kernel<2,false>, but the K/V tile is 96 keys so that BOTH query tiles get a
+// DOUBLE-BUFFERED logits accumulator in TMEM (4 x 96 + 2 x 64 columns = 512): S(j+2) is computed
+// while softmax works on S(j), so a softmax warpgroup never waits for the tensor core (with one
+// S buffer per tile it sat idle for the whole P -> PV -> QK^T round trip, ~1000 clk per tile:
+// profiles/r01g_exp_attn_phase_timing.txt).
+static constexpr int DB_BKV = 96;
+static constexpr int DB_KVT = DB_BKV * 128;       // bytes of one 96-row x 64-half swizzled tile
+static constexpr int DB_STAGES = 4;
+
+__global__ void __launch_bounds__(128 * 2 + 64, 1)
+ea_attn_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  // layout: Q[2] (16 KB each) | KV[DB_STAGES][K 12 KB | V 12 KB] | barriers
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + 2 * AT_ATOM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + DB_STAGES * 2 * DB_KVT);
+  uint64_t* q_full = bars;                          // [1]
+  uint64_t* kv_full = bars + 1;                     // [DB_STAGES]
+  uint64_t* kv_empty = kv_full + DB_STAGES;         // [DB_STAGES]
+  uint64_t* s_full = kv_empty + DB_STAGES;          // [2 tiles][2 buffers]
+  uint64_t* p_ready = s_full + 4;                   // [2][2] per (tile, logits buffer): a query tile's
+                                                    // softmax can run two key tiles ahead of the MMA warp
+                                                    // (stalled on the other tile), so one barrier per tile
+                                                    // would be overrun by a whole phase
+  uint64_t* o_done = p_ready + 4;                   // [2]
+  uint64_t* pv_prev = o_done + 2;                   // [2]  PV of the second-to-last tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_prev + 2);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Nkv + DB_BKV - 1) / DB_BKV;
+  constexpr int W_TMA = 8, W_MMA = 9;
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < DB_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&p_ready[2 * t], 128);
+      mbar_init(&p_ready[2 * t + 1], 128);
+      mbar_init(&o_done[t], 1);
+      mbar_init(&pv_prev[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  // TMEM columns: S[t][buf] at (2t + buf) * 96, O[t] at 384 + 64 t
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2u * AT_ATOM);
+      for (int t = 0; t < 2; ++t)
+        tma_load_4d(sQ + t * AT_ATOM, &tmQ, q_full, 0, head, (qb * 2 + t) * AT_BQ, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        uint8_t* sK = sKV + stage * 2 * DB_KVT;
+        mbar_expect_tx(&kv_full[stage], 2u * DB_KVT);
+        tma_load_4d(sK, &tmK, &kv_full[stage], 0, head, j * DB_BKV, b);
+        tma_load_4d(sK + DB_KVT, &tmV, &kv_full[stage], 0, head, j * DB_BKV, b);
+        if (++stage == DB_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == W_MMA) {
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_s = umma_idesc(128, DB_BKV, 0, 0);
+    const uint32_t idesc_o = umma_idesc(128, (uint32_t)p.dpad16, 0, 1);
+    const uint64_t dQ0 = umma_desc_k_sw128(smem_u32(sQ), 1024);
+    const uint64_t dK0 = umma_desc_k_sw128(smem_u32(sKV), 1024);
+    const uint64_t dV0 = umma_desc_mn_sw128(smem_u32(sKV) + DB_KVT, DB_KVT, 1024);
+    const int ksteps = p.ksteps;
+    auto issue_S = [&](int t, int stage, int buf) {
+      uint64_t dq = dQ0 + (uint64_t)(t * (AT_ATOM >> 4));
+      uint64_t dk = dK0 + (uint64_t)(stage * (2 * DB_KVT >> 4));
+      const uint32_t d = tb + (uint32_t)((2 * t + buf) * DB_BKV);
+      umma_f16_ss(d, dq, dk, idesc_s, 0u);
+      for (int ks = 1; ks < ksteps; ++ks) {
+        dq += 2; dk += 2;
+        umma_f16_ss(d, dq, dk, idesc_s, 1u);
+      }
+    };
+    auto issue_PV = [&](int t, int stage, int buf, bool first) {
+      uint64_t dv = dV0 + (uint64_t)(stage * (2 * DB_KVT >> 4));
+      const uint32_t d = tb + 384u + (uint32_t)(t * 64);
+      uint32_t pa = tb + (uint32_t)((2 * t + buf) * DB_BKV);
+      uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+      for (int ks = 0; ks < DB_BKV / 16; ++ks) {
+        umma_f16_ts(d, pa, dv, idesc_o, acc);
+        acc = 1u;
+        pa += 8u;
+        dv += (16 * 128) >> 4;
+      }
+    };
+    mbar_wait(q_full, 0);
+    // prologue: S(0) and S(1) of both tiles
+    for (int j = 0; j < 2 && j < n_tiles; ++j) {
+      mbar_wait(&kv_full[j], 0);
+      tc_fence_after();
+      EA_ISSUE(issue_S(0, j, j); umma_commit(&s_full[0 * 2 + j]); issue_S(1, j, j); umma_commit(&s_full[1 * 2 + j]));
+    }
+    int stage = 0;            // stage of K/V tile j
+    uint32_t phase = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int buf = j & 1;
+      const int j2 = j + 2;
+      int st2 = stage + 2;    // stage of tile j + 2
+      uint32_t ph2 = phase;
+      if (st2 >= DB_STAGES) { st2 -= DB_STAGES; ph2 ^= 1u; }
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[2 * t + buf], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        EA_ISSUE(issue_PV(t, stage, buf, j == 0);
+                 if (j + 1 == n_tiles) umma_commit(&o_done[t]);
+                 if (j + 2 == n_tiles) umma_commit(&pv_prev[t]);
+                 if (t == 1) umma_commit(&kv_empty[stage]));
+        if (j2 < n_tiles) {
+          if (t == 0) {
+            mbar_wait(&kv_full[st2], ph2);
+            tc_fence_after();
+          }
+          EA_ISSUE(issue_S(t, st2, buf); umma_commit(&s_full[t * 2 + buf]));
+        }
+      }
+      if (++stage == DB_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ======================= softmax warpgroups (tile t = warp >> 2) =====================
+    const int t = warp >> 2;
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int q = (qb * 2 + t) * AT_BQ + r;
+    const bool row_ok = q < p.Nq;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t tmem_O = tmem_base + lane_off + 384u + (uint32_t)(t * 64);
+    float m_run = -INFINITY;
+    float l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[t * 2 + buf], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tmem_S = tmem_base + lane_off + (uint32_t)((2 * t + buf) * DB_BKV);
+      const int valid = min(DB_BKV, p.Nkv - j * DB_BKV);
+      uint32_t v[3][32];
+      tmem_ld32(tmem_S, v[0]);
+      tmem_ld32(tmem_S + 32u, v[1]);
+      tmem_ld32(tmem_S + 64u, v[2]);
+      tmem_ld_wait();
+      if (valid < DB_BKV) {
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (h * 32 + i >= valid) v[h][i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[2][i]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), mx2) * p.scale_log2;
+      float alpha = 1.f;
+      const bool need = m_tile > m_run + 8.f;
+      if (need) {
+        alpha = ex2_approx(m_run - m_tile);
+        m_run = m_tile;
+        l *= alpha;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // O must hold tiles 0..j-1: PV(j-1) retires before S(j+1) does (same in-order MMA queue);
+        // on the last tile the epilogue barrier is the only later event
+        if (j + 1 < n_tiles) mbar_wait(&s_full[t * 2 + ((j + 1) & 1)], (uint32_t)(((j + 1) >> 1) & 1));
+        else mbar_wait(&pv_prev[t], 0u);   // last tile: no S(j+1) exists; PV(j-1) signals by itself
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < p.dpad16; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tmem_O + (uint32_t)c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem_O + (uint32_t)c, o);
+        }
+        tmem_st_wait();
+      }
+      const float neg_m = -m_run;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[h][i]), p.scale_log2, neg_m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[h][i + 1]), p.scale_log2, neg_m));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(v[h][i + 2]), p.scale_log2, neg_m));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(v[h][i + 3]), p.scale_log2, neg_m));
+          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+          pk[i >> 1] = ea_pack2(e0, e1);
+          pk[(i >> 1) + 1] = ea_pack2(e2, e3);
+        }
+        tmem_st16(tmem_S + (uint32_t)(h * 16), pk);
+      }
+      l += (s0 + s1) + (s2 + s3);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[2 * t + buf]);
+    }
+    mbar_wait(&o_done[t], 0u);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    ea_half* orow = p.out + (long long)b * p.o_bs + (long long)(row_ok ? q : 0) * p.o_ns +
+                    (long long)head * p.d;
+#pragma unroll 1
+    for (int c = 0; c < p.dpad16; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + (uint32_t)c, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            uint4 u = make_uint4(
+                ea_pack2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l),
+                ea_pack2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l),
+                ea_pack2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l),
+                ea_pack2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 static int encode_qkv(CUtensorMap* m, const void* base, int d, int heads, int N, int B,
-                      long long ns, long long bs) {
+                      long long ns, long long bs, int box_rows = 128) {
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)ns * 2, (cuuint64_t)bs * 2};
-  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = ea_tmap_encode()(m, EA_TMAP_DTYPE, 4, const_cast<void*>(base), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -532,6 +794,30 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
   p.out = reinterpret_cast<ea_half*>(a->out);
   p.o_bs = a->o_bs; p.o_ns = a->o_ns;
   p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.rel_s = a->rel_s;
+
+  // long sequences with small heads: double-buffered logits (ea_attn_db_kernel)
+  static const int db_env = [] { const char* e = getenv("EA_ATTN_DB"); return e ? atoi(e) : 1; }();
+  if (db_env && !a->rel_h && a->d <= 64 && !force_p_smem && force_nqt == 0 && a->Nkv >= 4 * DB_BKV &&
+      (db_env == 2 || (long long)((a->Nq + 2 * AT_BQ - 1) / (2 * AT_BQ)) * a->heads * a->B >= 148)) {
+    CUtensorMap tq, tk, tv;
+    if (encode_qkv(&tq, a->q, a->d, a->heads, a->Nq, a->B, a->q_ns, a->q_bs)) return EA_ERR_TMAP;
+    if (encode_qkv(&tk, a->k, a->d, a->heads, a->Nkv, a->B, a->k_ns, a->k_bs, DB_BKV)) return EA_ERR_TMAP;
+    if (encode_qkv(&tv, a->v, a->d, a->heads, a->Nkv, a->B, a->v_ns, a->v_bs, DB_BKV)) return EA_ERR_TMAP;
+    const int smem_bytes = 2 * AT_ATOM + DB_STAGES * 2 * DB_KVT + (1 + 2 * DB_STAGES + 12) * 8 + 16 + 1024;
+    static int db_set = 0;
+    if (!db_set) {
+      if (cudaFuncSetAttribute(ea_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
+          cudaSuccess)
+        return EA_ERR_CUDA;
+      db_set = 1;
+    }
+    dim3 grid((unsigned)((a->Nq + 2 * AT_BQ - 1) / (2 * AT_BQ)), (unsigned)a->heads, (unsigned)a->B);
+    if (ea_launch(ea_attn_db_kernel, grid, dim3(128 * 2 + 64), (size_t)smem_bytes, stream, tq, tk, tv, p) !=
+        cudaSuccess)
+      return EA_ERR_CUDA;
+    ea_count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : EA_ERR_CUDA;
+  }
 
   // two query tiles per CTA when both accumulators fit TMEM (d <= 128) and there is a second tile
   int nqt = (a->Nq > AT_BQ && p.dpad16 <= 128) ? 2 : 1;

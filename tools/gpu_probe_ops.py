@@ -326,6 +326,16 @@ def case_attn_d40_self():
     return _attn_case(2, 8, 4096, 4096, 40, fused=True)
 
 
+def case_attn_db_long():
+    """Double-buffered-logits kernel (d <= 64, >= 384 keys): ragged key count (last 96-key tile partial),
+    d = 40 and d = 64, more than one CTA wave."""
+    r1 = _attn_case(2, 8, 4096, 4000, 40)
+    r2 = _attn_case(1, 10, 2304, 2304, 64)
+    r3 = _attn_case(2, 8, 2300, 400, 40)
+    w = max(r["max_abs"] for r in (r1, r2, r3))
+    return {"max_abs": w, "ref_max": max(r["ref_max"] for r in (r1, r2, r3)), "rel_fro": max(r["rel_fro"] for r in (r1, r2, r3))}
+
+
 def case_attn_d80_self():
     return _attn_case(2, 8, 1024, 1024, 80)
 
