@@ -7,19 +7,25 @@
 //
 // One CTA = one (batch, head) and NQT query tiles of 128 rows (NQT = 2: two tiles ping-pong so
 // the tensor core works on one tile's MMAs while the other tile is in softmax; NQT = 1: one
-// tile with a double-buffered logits accumulator).  Warp roles (128 + 128*NQT threads, 1 CTA/SM):
-//   warp 0     TMA producer: Q tiles once, then K/V tiles of 128 keys into a `stages`-deep ring.
-//              Head dims that are not a multiple of 64 (40, 80, 160) are zero-padded for free by
-//              TMA out-of-bounds fill (tensor-map inner extent d, box 64 wide).
-//   warp 1     TMEM allocator + MMA issuer (one lane): S = Q K^T (M=128, N=128, K=d) into TMEM;
-//              O += P V (M=128, N=d, K=128) with P read straight from TMEM (tcgen05.mma A operand
-//              in tensor memory) and V consumed as an MN-major B operand from its row-major tile.
-//   warps 4..  softmax warpgroups, thread <-> query row: tcgen05.ld the logits, two passes
-//              (row max, then exp2 with the folded scale), P packed to 16-bit and written back over
+// tile with a double-buffered logits accumulator).  Warp roles (128*NQT + 64 threads, 1 CTA/SM);
+// the two control warps get the HIGHEST warp ids because the SM's warp arbiter prefers them:
+//   warps 0 .. 4*NQT-1   softmax warpgroups, thread <-> query row: one tcgen05.ld round trip brings
+//              the whole 128-column logits row into registers; row max, exp2 with the folded scale
+//              (+ the SAM rel-pos bias in the BIAS kernels), P packed to 16-bit and written back over
 //              the logits' own TMEM columns (tcgen05.st); O is rescaled in TMEM only when the
 //              running max moves by more than 2^8 (exact: the final 1/l uses the same max).
 //              Final 1/l normalisation and 16-byte stores.
+//   warp 4*NQT     TMA producer: Q tiles once, then K/V tiles into a `stages`-deep ring.
+//              Head dims that are not a multiple of 64 (40, 80, 160) are zero-padded for free by
+//              TMA out-of-bounds fill (tensor-map inner extent d, box 64 wide).
+//   warp 4*NQT+1   TMEM allocator + MMA issuer, warp-uniform control flow with one elected lane
+//              (a single-lane branch makes the compiler wrap every MMA in an ELECT/R2UR waterfall):
+//              S = Q K^T (M=128, N=keys, K=d) into TMEM; O += P V (M=128, N=d, K=keys) with P read
+//              straight from TMEM (tcgen05.mma A operand in tensor memory) and V consumed as an
+//              MN-major B operand from its row-major tile.
 // TMEM map (512 columns): NQT=2: S_A 0, S_B 128, O_A 256, O_B 384;  NQT=1: S[0] 0, S[1] 128, O 256.
+// ea_attn_db_kernel (d <= 64, no bias, >= 384 keys): 96-key tiles, so BOTH query tiles have two
+// logits buffers: S[t][buf] at (2t+buf)*96, O[t] at 384 + 64t; 4-stage K/V ring.
 #include <stdlib.h>
 #include "ea_common.cuh"
 #include "ea_internal.h"

@@ -105,6 +105,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// L2 prefetch of one box (no shared memory, no barrier): a hint, out-of-range boxes are harmless
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
                                             int c1) {
   asm volatile(
@@ -339,9 +346,33 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 
 // --------------------------------- math ------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// Compact forms on purpose: these are inlined 32x per epilogue chunk, and with IEEE division / libdevice
+// erff they were HALF of the GEMM kernel's 240 KB of SASS - the epilogue ran out of the instruction
+// cache whenever launches of different shapes alternated (profiles/r01o).
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float x) {
+  return x * mufu_rcp(1.0f + mufu_ex2(x * -1.4426950408889634f));
+}
+// exact-erf GELU (F.gelu default) with erf from Abramowitz & Stegun 7.1.26, |abs err| < 1.5e-7:
+// erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.  ~17 instructions.
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = mufu_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = fmaf(-poly * t, mufu_ex2(z * z * -1.4426950408889634f), 1.0f);   // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

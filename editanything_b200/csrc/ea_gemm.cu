@@ -68,6 +68,7 @@ struct GemmKParams {
   int pair_release;  // stages are released to the producer two at a time (even stage count >= 4)
   float* ws;   // [tiles][splits][128][BN] fp32
   int* cnt;    // [tiles][2]: arrived, done (zero between launches)
+  int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
 __device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n0, int& h0,
@@ -123,10 +124,93 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+// Out-of-line activation for the rarely taken paths (general / split-K epilogues, SiLU): one copy of
+// the code instead of 32 inlined ones per site keeps the kernel image small (instruction cache).
+__device__ __noinline__ float act_call(float x, int act) {
+  return act == EA_ACT_SILU ? silu_f(x) : gelu_erf_f(x);
+}
+
+// Coalesced tile stores.  A thread owns one accumulator row, so a direct store instruction touches 32
+// different rows (32 half-written sectors per instruction; measured: the epilogue of a 128x160 tile
+// took 4.9 us, longer than its 5-K-block main loop).  Instead every epilogue warp transposes its
+// 32 rows x 64 columns through a private 4 KB block of the (by then free) stage-0 A tile, XOR-swizzled
+// in 16-byte pieces, and writes each row's 128 bytes with 8 consecutive lanes.
+__device__ __forceinline__ void stage_put32(uint4* stg, int lane, int half, const uint4 (&o)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) stg[lane * 8 + ((half * 4 + q) ^ (lane & 7))] = o[q];
+}
+__device__ __forceinline__ void stage_flush(const uint4* stg, int lane, ea_half* out, long long ldo,
+                                            ea_half* out2, long long ldo2, long long m_mine, bool ok_mine,
+                                            int col0, int pieces, int n_limit, long long lin_m0, int M) {
+  __syncwarp();
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int col = col0 + piece * 8;
+#pragma unroll 1   // rolled on purpose: run once per 64 columns from a cold instruction cache
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + rsub;
+    long long m_r;
+    int ok_r;
+    if (lin_m0 >= 0) {   // linear GEMM: the warp's rows are consecutive - no shuffles on the latency chain
+      m_r = lin_m0 + row;
+      ok_r = m_r < M;
+    } else {
+      m_r = __shfl_sync(0xffffffffu, m_mine, row);
+      ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
+    }
+    if (ok_r && piece < pieces && col < n_limit) {
+      const uint4 val = stg[row * 8 + (piece ^ (row & 7))];
+      *reinterpret_cast<uint4*>(out + m_r * ldo + col) = val;
+      if (out2) *reinterpret_cast<uint4*>(out2 + m_r * ldo2 + col) = val;
+    }
+  }
+  __syncwarp();
+}
+
+// Coalesced load of a 32-row x 64-column group of the residual: lane -> (row 4i + lane/8, 16-byte piece
+// lane%8), so 8 consecutive lanes read one row's 128 bytes.  Rows come from the owning lanes by shuffle.
+__device__ __forceinline__ void residual_load64(uint4 (&rr)[8], const ea_half* residual, long long ldr,
+                                                int lane, long long m_mine, bool ok_mine, int col0,
+                                                int cols_left, int n_limit, long long lin_m0, int M) {
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int col = col0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + rsub;
+    long long m_r;
+    int ok_r;
+    if (lin_m0 >= 0) {
+      m_r = lin_m0 + row;
+      ok_r = m_r < M;
+    } else {
+      m_r = __shfl_sync(0xffffffffu, m_mine, row);
+      ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
+    }
+    rr[i] = (ok_r && piece * 8 < cols_left && col < n_limit)
+                ? __ldg(reinterpret_cast<const uint4*>(residual + m_r * ldr + col))
+                : make_uint4(0, 0, 0, 0);
+  }
+}
+
 // GEGLU: value chunk fx (tile columns c..c+31), gate chunk fg (tile columns BN/2+c..): out = x*gelu(g)
-__device__ __forceinline__ void epilogue_geglu32(const GemmKParams& p, const RowInfo& ri, int ncol0,
-                                                 int half_bn, int c, float (&fx)[32],
-                                                 float (&fg)[32]) {
+__device__ __forceinline__ void epilogue_geglu32(const float* cb, int half_bn, int c, float (&fx)[32],
+                                                 float (&fg)[32], uint4 (&o)[4]) {
+  uint32_t packed[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float2 bx = *reinterpret_cast<const float2*>(cb + c + j);
+    const float2 bg = *reinterpret_cast<const float2*>(cb + half_bn + c + j);
+    const float x0 = fx[j] + bx.x, x1 = fx[j + 1] + bx.y, g0 = fg[j] + bg.x, g1 = fg[j + 1] + bg.y;
+    packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+}
+
+// split-K reduce path: one thread = one (row, 32-column) unit, bias from global, direct stores
+__device__ __forceinline__ void epilogue_geglu32_direct(const GemmKParams& p, const RowInfo& ri, int ncol0,
+                                                        int half_bn, int c, float (&fx)[32],
+                                                        float (&fg)[32]) {
   const int nout0 = (ncol0 >> 1) + c;  // output column of element 0
   if (!(ri.ok && nout0 < (p.N >> 1))) return;
   uint32_t packed[16];
@@ -139,7 +223,7 @@ __device__ __forceinline__ void epilogue_geglu32(const GemmKParams& p, const Row
       g0 += __ldg(p.bias + ncol0 + half_bn + c + j);
       g1 += __ldg(p.bias + ncol0 + half_bn + c + j + 1);
     }
-    packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+    packed[j >> 1] = ea_pack2(x0 * act_call(g0, EA_ACT_GELU), x1 * act_call(g1, EA_ACT_GELU));
   }
   uint4* dst = reinterpret_cast<uint4*>(p.out + ri.m * p.ldo + nout0);
 #pragma unroll
@@ -173,10 +257,10 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const Row
   }
   if (p.act == EA_ACT_SILU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+    for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_SILU);
   } else if (p.act == EA_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+    for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_GELU);
   }
   if (p.out_scale != 1.0f) {
 #pragma unroll
@@ -240,9 +324,20 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const Row
 __device__ long long ea_gemm_dbg[64 * 4 + 8];
 #define EA_GT(idx, slot) do { if (dbg_cta && (idx) < 64 && (threadIdx.x & 31) == 0) ea_gemm_dbg[(idx) * 4 + (slot)] = clock64(); } while (0)
 #define EA_GT1(slot) do { if (dbg_cta) ea_gemm_dbg[256 + (slot)] = clock64(); } while (0)
+// Launch-chain stamps (%globaltimer, ns) per launch ordinal: CTA (0,0,0): 0 entry, 1 setup done,
+// 2 released by griddepcontrol.wait, 3 first operands landed, 4 accumulator complete, 5 epilogue done;
+// grid-wide: 6 = earliest CTA entry, 7 = latest CTA exit.
+__device__ unsigned long long ea_gemm_chain[1024 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EA_CH(slot) do { if (dbg_cta && p.dbg_id < 1024) ea_gemm_chain[p.dbg_id * 8 + (slot)] = gtimer(); } while (0)
 #else
 #define EA_GT(idx, slot) do {} while (0)
 #define EA_GT1(slot) do {} while (0)
+#define EA_CH(slot) do {} while (0)
 #endif
 
 // TWO = true: CTA pairs (cluster of 2 along M) run tcgen05.mma.cta_group::2 with M = 256; each CTA
@@ -276,7 +371,11 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int tn = blockIdx.y;
 #ifdef EA_GEMM_TIMING
   const bool dbg_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  if (threadIdx.x == 0) EA_GT1(0);
+  if (threadIdx.x == 0) {
+    EA_GT1(0);
+    EA_CH(0);
+    if (p.dbg_id < 1024) atomicMin(&ea_gemm_chain[p.dbg_id * 8 + 6], gtimer());
+  }
 #endif
   const int nkb_total = p.nkb_main + p.nkb_extra;
   const int kb0 = blockIdx.z * p.kb_per_split;
@@ -309,9 +408,12 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (TWO) cluster_sync_all();   // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef EA_GEMM_TIMING
+  if (threadIdx.x == 0) EA_CH(1);
+#endif
   pdl_wait();  // everything above overlapped the previous kernel's tail
 #ifdef EA_GEMM_TIMING
-  if (threadIdx.x == 0) EA_GT1(1);
+  if (threadIdx.x == 0) { EA_GT1(1); EA_CH(2); }
 #endif
 
   if (warp == W_TMA) {
@@ -405,6 +507,9 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         EA_GT(kb - kb0, 2);
+#ifdef EA_GEMM_TIMING
+        if (kb == kb0 && lane == 0) EA_CH(3);
+#endif
         const uint64_t db = da + ab16;
         const bool release = !pair_release || (stage & 1) || (kb + 1 == kb1);
         uint64_t* ebar = &empty_bar[pair_release ? (stage | 1) : stage];
@@ -451,8 +556,9 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // flight (before: four dependent global round trips per 32-column chunk, ~5400 clk per tile).
     const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
     const bool fast = p.splits == 1 && !geglu && !p.out_f32 && !p.accumulate && (b_last - b_first) <= 1;
-    uint4 rnext[4];
-    const ea_half* res_row = nullptr;
+    uint4 rres[8];   // next 64-column group of the residual (coalesced layout)
+    const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
+    const bool has_res = p.residual != nullptr;
     if (fast) {
       for (int i = et; i < p.BN; i += 128) {
         const int col = ncol0 + i;
@@ -465,39 +571,42 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         cb[i] = v0;
         cb[256 + i] = v1;
       }
-      if (p.residual && ri.ok) {
-        res_row = p.residual + ri.m * p.ldr + ncol0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          rnext[q] = (ncol0 + q * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row) + q)
-                                           : make_uint4(0, 0, 0, 0);
-      }
+      if (has_res) residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0, p.BN, p.N, lin_m0, p.M);
+      epi_bar_sync();
+    } else if (geglu && p.splits == 1) {
+      for (int i = et; i < p.BN; i += 128)
+        cb[i] = (p.bias && ncol0 + i < p.N) ? __ldg(p.bias + ncol0 + i) : 0.f;
       epi_bar_sync();
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #ifdef EA_GEMM_TIMING
-    if (threadIdx.x == 0) EA_GT1(6);
+    if (threadIdx.x == 0) { EA_GT1(6); EA_CH(4); }
 #endif
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    // accumulator complete => every MMA has retired and every TMA load was consumed: stage 0 is free
+    uint4* stg = reinterpret_cast<uint4*>(smem + wq * 4096);
+    uint4* stg2 = reinterpret_cast<uint4*>(smem + 16384 + wq * 4096);   // >= 2 stages of >= 18 KB exist
     if (fast) {
       const float* cbr = cb + (ri.batch != b_first ? 256 : 0);
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c, v);
-        uint4 rcur[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+      // one 32-column chunk: residual hand-off, bias / activation / scale / residual, staging, flush
+      auto process = [&](const uint32_t (&v)[32], const int c) {
         const int n_first = ncol0 + c;
-        if (res_row && c + 32 < p.BN) {  // next chunk's residual: in flight during this chunk
+        const int half = (c >> 5) & 1;
+        if (has_res && half == 0) {
+          // hand the prefetched group to its rows through the second staging block, then put the
+          // next group's loads in flight
+          const int piece = lane & 7, rsub = lane >> 3;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            rnext[q] = (n_first + 32 + q * 8 < p.N)
-                           ? __ldg(reinterpret_cast<const uint4*>(res_row + c + 32) + q)
-                           : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rsub;
+            stg2[row * 8 + (piece ^ (row & 7))] = rres[i];
+          }
+          __syncwarp();
+          if (c + 64 < p.BN)
+            residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, n_first + 64, p.BN - c - 64, p.N, lin_m0, p.M);
         }
-        tmem_ld_wait();
-        if (ri.ok && n_first < p.N) {
+        {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -509,7 +618,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (p.act == EA_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_SILU);
           } else if (p.act == EA_ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
@@ -518,28 +627,34 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
           }
-          if (res_row) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float2 a = ea_unpack2(rcur[q].x), b = ea_unpack2(rcur[q].y), cc = ea_unpack2(rcur[q].z),
-                     d = ea_unpack2(rcur[q].w);
+          for (int q = 0; q < 4; ++q) {
+            const int slot = lane * 8 + ((half * 4 + q) ^ (lane & 7));
+            if (has_res) {
+              const uint4 rc = stg2[slot];
+              const float2 a = ea_unpack2(rc.x), b = ea_unpack2(rc.y), cc = ea_unpack2(rc.z), d = ea_unpack2(rc.w);
               f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
               f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
             }
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + ri.m * p.ldo + n_first);
-          uint4* dst2 = p.out2 ? reinterpret_cast<uint4*>(p.out2 + ri.m * p.ldo2 + n_first) : nullptr;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n_first + q * 8 < p.N) {
-              const uint4 o = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
-                                         ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
-              dst[q] = o;
-              if (dst2) dst2[q] = o;
-            }
+            stg[slot] = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                   ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
           }
         }
-        __syncwarp();
+        if (half == 1 || c + 32 >= p.BN)
+          stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
+                      half == 1 ? 8 : 4, p.N, lin_m0, p.M);
+      };
+      // TMEM loads are double-buffered: the next chunk's tcgen05.ld is in flight while this chunk is
+      // converted and stored (one warp per SM sub-partition: nothing else hides the load latency)
+      // (one copy of the chunk body: vb is moved into va instead of instantiating `process` twice)
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, vb);
+      for (int c = 0; c < p.BN; c += 32) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) va[j] = vb[j];
+        if (c + 32 < p.BN) tmem_ld32(taddr + (uint32_t)(c + 32), vb);
+        process(va, c);
       }
     } else
     if (p.splits == 1) {
@@ -553,8 +668,13 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           float fx[32], fg[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
-          epilogue_geglu32(p, ri, ncol0, half_bn, c, fx, fg);
-          __syncwarp();
+          uint4 o[4];
+          epilogue_geglu32(cb, half_bn, c, fx, fg, o);
+          const int half = (c >> 5) & 1;
+          stage_put32(stg, lane, half, o);
+          if (half == 1 || c + 32 >= half_bn)
+            stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c - half * 32,
+                        half == 1 ? 8 : 4, p.N >> 1, lin_m0, p.M);
         }
       } else {
         for (int c = 0; c < p.BN; c += 32) {
@@ -666,7 +786,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               float4 v = sp[8 + j];
               fg[4 * j] = v.x; fg[4 * j + 1] = v.y; fg[4 * j + 2] = v.z; fg[4 * j + 3] = v.w;
             }
-            epilogue_geglu32(p, r2, ncol0, half_bn, c, f, fg);
+            epilogue_geglu32_direct(p, r2, ncol0, half_bn, c, f, fg);
           } else {
             epilogue_chunk32(p, r2, ncol0 + c, f);
           }
@@ -690,7 +810,11 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 
 #ifdef EA_GEMM_TIMING
-  if (threadIdx.x == 0) EA_GT1(7);
+  if (threadIdx.x == 0) {
+    EA_GT1(7);
+    EA_CH(5);
+    if (p.dbg_id < 1024) atomicMax(&ea_gemm_chain[p.dbg_id * 8 + 7], gtimer());
+  }
 #endif
   tc_fence_before();
   __syncthreads();
@@ -746,8 +870,22 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // every SM has one deep pipeline, and the partial tiles are combined in-kernel (see the epilogue).
 struct GemmPlan { int BN, stages, splits, kbps, occ; double cost; int two; };
 
+// Constants fitted (tools/fit/fit_planner.py, log-RMSE 0.14) to the tile sweep of the step's dominant
+// shapes, profiles/r01n_exp_gemm_sweep.json; the per-launch phases behind them are in
+// profiles/r01n_exp_gemm_chain.txt: a CTA pays ~3800 clk before its first MMA (setup, dependency
+// release, first TMA round trip; +2100 for a CTA pair's cluster syncs) and ~50 clk per accumulator
+// column in the epilogue (+21 with a residual) because ONE warp per SM sub-partition drains TMEM,
+// converts and stores with nothing to hide its instruction latencies.
+static constexpr double PL_LAT = 2100.0, PL_SM_CAP = 57.0, PL_L2 = 8000.0, PL_HBM = 3400.0;
+#ifndef PL_SPLIT_COL
+#define PL_SPLIT_COL 8.0
+#define PL_SPLIT_FIX 7000.0
+#endif
+static constexpr double PL_START = 3800.0, PL_START_TWO = 2100.0, PL_EPI = 50.0, PL_EPI_RES = 21.0;
+
 static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm,
-                          bool allow_two) {
+                          bool allow_two, bool has_res = false) {
+  const double epi_col = (PL_EPI + (has_res ? PL_EPI_RES : 0.0)) * (act == EA_ACT_GEGLU ? 0.84 : 1.0);
   // measured on B200 (profiles/r01c): one SM fills shared memory at ~45 B/clk whatever the tile
   // shape (cuBLAS sits at the same cap with 2-CTA 256x256 tiles), the chip at ~6000 B/clk from L2
   // and ~3400 B/clk from HBM; a tcgen05 128xBNx16 MMA takes BN/2 clk.
@@ -775,14 +913,16 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
         const long long conc = ctas < slots ? ctas : slots;
         const int per_sm = (int)((conc + n_sm - 1) / n_sm);
         const double t_mma = 0.5 * BN * 4 * per_sm;
-        const double t_sm = (double)stage_bytes * per_sm / 52.0;
-        const double t_chip = (double)conc * stage_bytes / 6000.0;
-        const double t_lat = 1800.0 / st;
+        const double t_sm = (double)stage_bytes * per_sm / PL_SM_CAP;
+        const double hbm_frac = 1.0 / (double)mt;
+        const double t_chip = (double)conc * (BM * BK * 2.0 / PL_L2 + (BN / 2) * BK * 2.0 * hbm_frac / PL_HBM +
+                                              (BN / 2) * BK * 2.0 * (1.0 - hbm_frac) / PL_L2);
+        const double t_lat = PL_LAT / st;
         double t_kb = t_mma;
         if (t_sm > t_kb) t_kb = t_sm;
         if (t_chip > t_kb) t_kb = t_chip;
         if (t_lat > t_kb) t_kb = t_lat;
-        const double cost = (double)waves * (nkb * t_kb + 4200.0 + 8.0 * BN);
+        const double cost = (double)waves * (PL_START + PL_START_TWO + nkb * t_kb + epi_col * BN);
         if (cost < best.cost) best = {BN, st, 1, nkb, occ, cost, 1};
       }
     }
@@ -819,19 +959,25 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
         const long long conc = ctas < slots ? ctas : slots;
         const int per_sm = (int)((conc + n_sm - 1) / n_sm);
         const double t_mma = 0.5 * BN * 4 * per_sm;                       // 4 MMAs (K=16) per K-block
-        const double t_sm = (double)stage_bytes * per_sm / 52.0;          // per-SM TMA fill cap
+        const double t_sm = (double)stage_bytes * per_sm / PL_SM_CAP;      // per-SM TMA fill cap
         const double a_bytes = BM * BK * 2.0, b_bytes = BN * BK * 2.0;
         const double hbm_frac = 1.0 / (double)mt;                         // weights: HBM once, then L2
-        const double t_chip = (double)conc * (a_bytes / 6000.0 + b_bytes * hbm_frac / 3400.0 +
-                                              b_bytes * (1.0 - hbm_frac) / 6000.0);
-        const double t_lat = 1800.0 / st;
+        const double t_chip = (double)conc * (a_bytes / PL_L2 + b_bytes * hbm_frac / PL_HBM +
+                                              b_bytes * (1.0 - hbm_frac) / PL_L2);
+        const double t_lat = PL_LAT / st;
         double t_kb = t_mma;
         if (t_sm > t_kb) t_kb = t_sm;
         if (t_chip > t_kb) t_kb = t_chip;
         if (t_lat > t_kb) t_kb = t_lat;
-        double cost = (double)waves * (kbps * t_kb + 3500.0 + 8.0 * BN);
-        // partial store + barrier + distributed reduce (fitted to tools/exp_splitk.py, r01g)
-        if (splits > 1) cost += 3500.0 + 3.0 * (BM * BN * 4.0) / 25.0 + 150.0 * splits;
+        double cost;
+        if (splits == 1) {
+          cost = (double)waves * (PL_START + kbps * t_kb + epi_col * BN);
+        } else {
+          // fp32 partial store, arrival counter, distributed reduce + fused epilogue (tools/exp_splitk.py,
+          // r01g; the chain stamps of the 8x8 conv put the whole fix-up at ~22k clk for splits = 10, BN = 96)
+          cost = (double)waves * (PL_START + kbps * t_kb + PL_SPLIT_COL * BN) + PL_SPLIT_FIX +
+                 3.0 * (BM * BN * 4.0) / 25.0 + 150.0 * splits;
+        }
         if (cost < best.cost) best = {BN, st, splits, kbps, occ, cost, 0};
       }
     }
@@ -857,6 +1003,19 @@ static int sm_count() {
 using namespace ea;
 
 #ifdef EA_GEMM_TIMING
+static int g_dbg_launch = 0;
+extern "C" int ea_gemm_chain_reset(void) {
+  static unsigned long long init[1024 * 8];
+  for (int i = 0; i < 1024; ++i)
+    for (int j = 0; j < 8; ++j) init[i * 8 + j] = j == 6 ? ~0ull : 0ull;
+  g_dbg_launch = 0;
+  return cudaMemcpyToSymbol(ea_gemm_chain, init, sizeof(init)) == cudaSuccess ? 0 : EA_ERR_CUDA;
+}
+extern "C" int ea_gemm_chain_read(unsigned long long* host_out, int n_launches) {
+  if (n_launches > 1024) n_launches = 1024;
+  return cudaMemcpyFromSymbol(host_out, ea_gemm_chain, sizeof(unsigned long long) * 8 * n_launches) == cudaSuccess
+             ? 0 : EA_ERR_CUDA;
+}
 extern "C" int ea_gemm_debug_read(long long* host_out, int n) {
   if (n > 64 * 4 + 8) n = 64 * 4 + 8;
   return cudaMemcpyFromSymbol(host_out, ea_gemm_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : EA_ERR_CUDA;
@@ -882,6 +1041,9 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
 
   GemmKParams p;
   memset(&p, 0, sizeof(p));
+#ifdef EA_GEMM_TIMING
+  p.dbg_id = g_dbg_launch++;
+#endif
   p.M = a->M;
   p.N = a->N;
   p.mode = a->mode;
@@ -968,7 +1130,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
   static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
   const bool can_two = a->mode != EA_GEMM_CONV_S2 && two_env != 0 && a->force_2cta >= 0;
-  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two);
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
   if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
     plan.two = 1; plan.splits = 1; plan.kbps = nkb;
     if (plan.BN < 64) plan.BN = 64;
