@@ -84,6 +84,25 @@ def make_inputs(cfg, B, lat, L, seed):
     return x, ctx, [h0.repeat(B, 1, 1, 1), h1.repeat(B, 1, 1, 1)]
 
 
+def _gemm_traffic():
+    """DRAM bytes per ea_gemm launch (read + write, averaged over one step's launches) from the committed
+    ncu launch list of this same command (profiles/gemm_traffic.json, written by
+    tools/summarize_launches.py --traffic-json); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        doc = json.load(open(path))
+        n = rd = 0
+        for k, v in doc["kernels"].items():
+            if "ea_gemm_kernel" in k:
+                n += v["launches"]
+                rd += v["dram_bytes_per_launch"] * v["launches"]
+        if n:
+            return round(rd / n), "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/gemm_traffic.json (" + doc.get("source", "") + ")"
+    except (OSError, KeyError, ValueError):
+        pass
+    return None, "no ncu capture committed"
+
+
 class GemmProbe:
     """Wraps editanything_b200.ops and records every ea_gemm call of one step (arguments + algorithmic
     FLOPs).  The recorded launches are then re-issued back to back inside ONE CUDA graph and the graph
@@ -230,8 +249,18 @@ def run_ours(args, rank, world, local_rank):
     for c, o in zip(eng.cns, eng_ops_saved[3]):
         c.ops = o
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # operand bytes the algorithm needs per launch (A + W + out (+ residual)), averaged over the step's launches
+    alg_bytes = 0
+    for a_, w_, out_, kw_, _ in probe.records:
+        conv = kw_.get("conv")
+        Mrows = conv[0] * conv[1] * conv[2] if conv else (kw_.get("M") or a_.shape[0])
+        Kin = conv[3] if conv else w_.shape[1]
+        n_out = w_.shape[0] // 2 if kw_.get("act") == 3 else w_.shape[0]
+        alg_bytes += 2 * (Mrows * Kin + w_.numel() + Mrows * n_out * (2 if kw_.get("residual") is not None else 1))
+    traffic, traffic_src = _gemm_traffic()
     roofline = {"bound": "tensor", "kernel": "ea_gemm_kernel", "achieved": round(achieved, 1), "peak": sust,
-                "unit": "TFLOP/s", "frac": round(achieved / sust, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / sust, 4), "traffic": traffic,
+                "traffic_note": traffic_src, "algorithmic_bytes_per_launch": round(alg_bytes / max(n_gemm, 1)),
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches": n_gemm, "gemm_ms_per_step": round(g_ms, 3),
                 "timing": "all ea_gemm launches of one step re-issued back to back in one CUDA graph, CUDA events",

@@ -1,6 +1,8 @@
 """Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: per-kernel totals and
 shares, plus (for ea_gemm_kernel) a per-grid-shape breakdown.  Usage:
-    python tools/summarize_launches.py gpurun_out/launches.csv [--top N]"""
+    python tools/summarize_launches.py gpurun_out/launches.csv [--top N] [--traffic-json out.json]
+With `--traffic-json` (launch list captured with dram__bytes_read.sum,dram__bytes_write.sum as well)
+the per-kernel DRAM bytes per launch are written as JSON; bench.py reports them as `roofline.traffic`."""
 import csv
 import collections
 import io
@@ -20,6 +22,24 @@ def load(path):
         ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1)
         out.append((r["Kernel Name"], r.get("Grid Size", ""), r.get("Block Size", ""), ns))
     return out
+
+
+def load_traffic(path):
+    """{kernel name: [launches, dram bytes read, dram bytes written]} from the same csv."""
+    txt = open(path, errors="replace").read()
+    i = txt.find('"ID"')
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.defaultdict(lambda: [set(), 0.0, 0.0])
+    for r in csv.DictReader(io.StringIO(txt[i:])):
+        m = r.get("Metric Name")
+        if m not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            continue
+        v = float(r["Metric Value"].replace(",", "")) * scale.get(r.get("Metric Unit", "byte"), 1)
+        name = r["Kernel Name"].split("(")[0].replace("void ", "").strip()
+        a = acc[name]
+        a[0].add(r["ID"])
+        a[1 if m.endswith("read.sum") else 2] += v
+    return {k: [len(v[0]), v[1], v[2]] for k, v in acc.items()}
 
 
 def main():
@@ -45,6 +65,21 @@ def main():
     print(f"{'kernel / grid':60s} {'n':>5s} {'ms':>9s} {'avg us':>8s}")
     for (name, g), (n, ns) in sorted(bg.items(), key=lambda kv: -kv[1][1])[:top]:
         print(f"{(name[:30] + ' ' + g)[:60]:60s} {n:5d} {ns / 1e6:9.3f} {ns / n / 1e3:8.2f}")
+
+
+    if "--traffic-json" in sys.argv:
+        import json
+        out = sys.argv[sys.argv.index("--traffic-json") + 1]
+        tr = load_traffic(path)
+        doc = {"source": path, "note": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
+               "one launch at a time (serialised, cold L2): per-launch averages",
+               "kernels": {k: {"launches": n, "dram_read_bytes_per_launch": rd / n, "dram_write_bytes_per_launch": wr / n,
+                               "dram_bytes_per_launch": (rd + wr) / n} for k, (n, rd, wr) in tr.items() if n}}
+        json.dump(doc, open(out, "w"), indent=1)
+        print()
+        print(f"{'kernel':44s} {'n':>5s} {'DRAM MB/launch':>15s}")
+        for k, v in sorted(doc["kernels"].items(), key=lambda kv: -kv[1]["dram_bytes_per_launch"] * kv[1]["launches"]):
+            print(f"{k[:44]:44s} {v['launches']:5d} {v['dram_bytes_per_launch'] / 1e6:15.3f}")
 
 
 if __name__ == "__main__":
