@@ -227,7 +227,24 @@ def run_ours(args, rank, world, local_rank):
     except ImportError:
         pass
 
-    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0)
+    # ---- first-stage decoder (once per image) -----------------------------------
+    vae_ms, vae = None, None
+    if not args.no_vae:
+        from editanything_b200.vae import SD_VAE, VaeDecoderEngine, make_vae_state_dict
+        vae = VaeDecoderEngine(SD_VAE, make_vae_state_dict(SD_VAE, 402, device=dev), dev)
+        lat = eng.latents().float()
+        for _ in range(2):
+            vae.decode_latents(lat)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            vae.decode_latents(lat)
+        s1.record()
+        torch.cuda.synchronize()
+        vae_ms = s0.elapsed_time(s1) / 3
+
+    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0) + (vae_ms or 0.0)
     value = world * 1000.0 / img_ms
 
     # ---- roofline of the dominant kernel (ea_gemm_kernel), live CUDA events ----------------------
@@ -289,6 +306,8 @@ def run_ours(args, rank, world, local_rank):
             eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
             for i in range(DDIM_STEPS):
                 eng.step(int(ts[i]), float(a[i]), float(ap[i]))
+            if vae is not None:
+                return vae.decode_latents(eng.latents().float()).cpu(), emb      # the decoded [1,3,512,512] image
             return eng.latents().cpu(), emb
 
         one_image()
@@ -313,8 +332,8 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": d2h // DDIM_STEPS,
                "ms_per_image": round(dt / n_img * 1e3, 2), "images_timed": n_img,
                "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host ctx / hints / "
-                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> D2H latents; 1 untimed warm-up "
-                       "image; VAE / text encoder / mask decoder not included (out of scope, SURVEY.md 8f)"}
+                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> VAE decode -> D2H fp32 image; "
+                       "1 untimed warm-up image; text encoder / SAM mask decoder / VAE encode not included (SURVEY.md 8f)"}
 
     line = {
         "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
@@ -327,6 +346,8 @@ def run_ours(args, rank, world, local_rank):
                    "global_batch": world, "parallelism": f"dp{world} (one image per GPU, final all-gather)",
                    "l2": "weights touched per step (3.16 GB) exceed the 126 MB L2; no explicit flush",
                    "cuda_graph": not args.no_graph, "sam_ms_per_image": sam_ms, "sam": sam_note,
+                   "vae_decode_ms_per_image": vae_ms,
+                   "image": "image_ms = 50 x ms_per_step + SAM encode + VAE decode (kl-f8 decoder, 64x64 -> 512x512)",
                    "image_ms": round(img_ms, 3), "outputs_finite": finite},
         "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roofline, "e2e": e2e,
@@ -386,6 +407,18 @@ def _oracle_sam_seconds():
     return time.perf_counter() - t0
 
 
+def _oracle_vae_seconds():
+    """One first-stage decode (latents 64x64 -> 512x512) of the CPU oracle, fp32 (~10-20 s)."""
+    from editanything_b200.vae_spec import SD_VAE, make_vae_state_dict
+    from oracle import vae_oracle as V
+    sd = make_vae_state_dict(SD_VAE, 402)
+    lat = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(4)) * SD_VAE.scaling_factor
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        V.decode_latents(lat, sd, SD_VAE)
+    return time.perf_counter() - t0
+
+
 def cpu_baseline(sample_steps=1):
     from editanything_b200.unet_spec import SD15
     cores = usable_cores()
@@ -397,11 +430,13 @@ def cpu_baseline(sample_steps=1):
         step()
     dt = (time.perf_counter() - t0) / sample_steps
     sam_s = _oracle_sam_seconds()
-    return {"value": round(1.0 / (DDIM_STEPS * dt + sam_s), 6), "unit": "images/s", "cores": cores, "kind": "port",
+    vae_s = _oracle_vae_seconds()
+    return {"value": round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6), "unit": "images/s", "cores": cores, "kind": "port",
             "ms_per_step": round(dt * 1e3, 1), "sam_ms_per_image": round(sam_s * 1e3, 1),
+            "vae_decode_ms_per_image": round(vae_s * 1e3, 1),
             "sample": f"{sample_steps} full-size fused step(s) (2 ControlNets + UNet + CFG + DDIM, B=2, 64x64, fp32) of the "
-                      f"oracle port on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode of the oracle port; "
-                      f"images/s = 1/(50*step + SAM)"}
+                      f"oracle port on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode + 1 VAE decode of the oracle "
+                      f"port; images/s = 1/(50*step + SAM + VAE)"}
 
 
 def run_reference(args, rank, world):
@@ -426,10 +461,11 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / k
     sam_s = _oracle_sam_seconds()
-    v = round(1.0 / (DDIM_STEPS * dt + sam_s), 6)
+    vae_s = _oracle_vae_seconds()
+    v = round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6)
     sample = (f"{k} of the requested {args.steps} steps timed (each a full-size configs[1] fused step on CPU, fp32, "
-              f"{cores} threads; bounded to ~{int(budget_s)} s) + 1 SAM ViT-H encode ({sam_s:.1f} s); "
-              f"images/s = 1/(50*step + SAM)")
+              f"{cores} threads; bounded to ~{int(budget_s)} s) + 1 SAM ViT-H encode ({sam_s:.1f} s) + 1 VAE decode "
+              f"({vae_s:.1f} s); images/s = 1/(50*step + SAM + VAE)")
     line = {"impl": "reference",
             "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
             "value": v, "unit": "images/s", "n_gpus": world, "steps": k, "warmup": 1 + n_w,
@@ -448,6 +484,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the first-stage decode (kernel profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")

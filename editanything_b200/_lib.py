@@ -82,6 +82,8 @@ SYMBOLS = {
     "ea_window_unpartition": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_sam_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_nhwc_to_nchw_f32": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ea_softmax_rows": (_I, [_P, _L, _P, _L, _I, _I, _P]),
+    "ea_image_out": (_I, [_P, _L, _P, _I, _L, _I, _F, _F, _F, _F, _P]),
 }
 
 _lib = None

@@ -572,6 +572,66 @@ __global__ void nhwc_to_nchw_f32_kernel(const ea_half* __restrict__ x, float* __
   }
 }
 
+// Row softmax of fp32 logits -> half probabilities (VAE AttnBlock: one head, d = 512, so the logits
+// go through two plain GEMMs instead of the flash kernel; ldm/modules/diffusionmodules/model.py:193-201).
+// One CTA per row, three passes over a row that stays in L1/L2 (<= 64 KB).
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, ea_half* __restrict__ p,
+                                    long long ldp, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  const float* row = s + (long long)blockIdx.x * lds;
+  ea_half* prow = p + (long long)blockIdx.x * ldp;
+  const int tid = threadIdx.x, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    sum += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+  }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    uint2 o;
+    o.x = ea_pack2(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+    o.y = ea_pack2(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    *reinterpret_cast<uint2*>(prow + i) = o;
+  }
+}
+
+// Decoded image: NHWC half (first C channels of rows `ldx` wide) -> fp32 NCHW, out = clamp(x*scale +
+// shift, lo, hi): decode_latents' (image / 2 + 0.5).clamp(0, 1) (utils/stable_diffusion_controlnet_
+// inpaint.py:718-724) fused with the layout change.  One thread per pixel, planes written coalesced.
+__global__ void image_out_kernel(const ea_half* __restrict__ x, long long ldx, float* __restrict__ out,
+                                 int B, long long HW, int C, float scale, float shift, float lo, float hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  const long long b = i / HW, pix = i - b * HW;
+  const ea_half* px = x + i * ldx;
+  for (int c = 0; c < C; ++c) {
+    const float v = fminf(fmaxf(fmaf(ea_h2f(px[c]), scale, shift), lo), hi);
+    out[(b * C + c) * HW + pix] = v;
+  }
+}
+
 // 3x3 stride-1 pad-1 convolution with a tiny input depth (conv_in: 4 -> 320, openaimodel.py:533-539,
 // and ControlNet `h = conv_in(x) + guided_hint`, cldm/cldm.py:293-297).  K = 9*Cin is far too small for
 // the tensor-core path; the whole filter bank lives in shared memory, a thread owns one pixel and 8
@@ -817,6 +877,25 @@ extern "C" int ea_nhwc_to_nchw_f32(const void* x, float* out, int B, int HW, int
   if (!x || !out) return EA_ERR_ARG;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
   ea_launch(nhwc_to_nchw_f32_kernel, dim3(grid), dim3(block), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(x), out, B, HW, C);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int cols,
+                               void* stream) {
+  if (!s || !p) return EA_ERR_ARG;
+  if (rows <= 0 || cols <= 0 || cols % 4 != 0 || lds % 4 != 0 || ldp % 4 != 0) return EA_ERR_SHAPE;
+  ea_launch(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), (size_t)0, EA_STREAM(stream), s, lds,
+            reinterpret_cast<ea_half*>(p), ldp, cols);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_image_out(const void* x, long long ldx, float* out, int B, long long HW, int C, float scale,
+                            float shift, float lo, float hi, void* stream) {
+  if (!x || !out) return EA_ERR_ARG;
+  if (B <= 0 || HW <= 0 || C <= 0 || ldx < C) return EA_ERR_SHAPE;
+  const long long total = (long long)B * HW;
+  ea_launch(image_out_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, EA_STREAM(stream),
+            reinterpret_cast<const ea_half*>(x), ldx, out, B, HW, C, scale, shift, lo, hi);
   return EA_LAUNCH_OK();
 }
 

@@ -238,3 +238,19 @@ def nhwc_to_nchw_f32(x, out, *, B, HW, C_):
     lib = L.lib()
     L.check(lib.ea_nhwc_to_nchw_f32(_p(x), _p(out), B, HW, C_, _stream()), "ea_nhwc_to_nchw_f32")
     return out
+
+
+def softmax_rows(s, p, *, rows, cols, lds=None, ldp=None):
+    """p = softmax(s, dim=-1): fp32 logits [rows, cols] -> half probabilities (VAE AttnBlock)."""
+    lib = L.lib()
+    L.check(lib.ea_softmax_rows(_p(s), lds if lds is not None else cols, _p(p), ldp if ldp is not None else cols,
+                                rows, cols, _stream()), "ea_softmax_rows")
+    return p
+
+
+def image_out(x, out, *, B, HW, C_, ldx, scale=0.5, shift=0.5, lo=0.0, hi=1.0):
+    """half NHWC rows (first C_ channels of ldx) -> fp32 NCHW, clamp(x * scale + shift, lo, hi)."""
+    lib = L.lib()
+    L.check(lib.ea_image_out(_p(x), ldx, _p(out), B, HW, C_, scale, shift, lo, hi, _stream()), "ea_image_out")
+    return out
+

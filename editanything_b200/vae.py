@@ -1,0 +1,206 @@
+"""First-stage (AutoencoderKL) decoder on the libea_b200 C-ABI operators — SURVEY.md §8f row N1, the
+step right after the denoising loop (`decode_latents`, utils/stable_diffusion_controlnet_inpaint.py:
+718-724: latents / scaling_factor -> vae.decode -> (x / 2 + 0.5).clamp(0, 1)).
+
+Reference semantics followed (paths relative to the reference root):
+    AutoencoderKL.decode          ldm/models/autoencoder.py:88-91      post_quant_conv (1x1) -> Decoder
+    Decoder.forward               ldm/modules/diffusionmodules/model.py:623-652
+    ResnetBlock.forward           model.py:129-148   GN(32, eps 1e-6) -> swish -> conv3x3 -> GN -> swish
+                                                     -> conv3x3, + x (or + nin_shortcut 1x1 (x))
+    AttnBlock.forward             model.py:181-210   GN -> q, k, v 1x1 -> softmax(q k^T C^-1/2) v -> proj, + x
+    Upsample.forward              model.py:60-64     nearest x2 -> conv3x3
+Execution: channels-last half activations, fp32 accumulation; every 3x3 convolution is the tcgen05
+implicit GEMM (ea_gemm CONV_S1), the 1x1 shortcut of a channel-changing ResnetBlock rides along as extra
+K columns of conv2, GroupNorm + swish is one fused launch, and the single-head d = 512 attention is two
+plain GEMMs around a row-softmax kernel (fp32 logits).  The last convolution (128 -> 3) is padded to 8
+output channels so it can use the same GEMM; `ea_image_out` drops the padding, applies
+(x / 2 + 0.5).clamp(0, 1) and writes the fp32 NCHW image the pipeline hands to numpy / PIL.
+"""
+import types
+
+import torch
+
+from . import _lib as L
+from . import ops as _cuda_ops
+from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, make_vae_state_dict  # noqa: F401
+
+
+def _conv3_pack(w):  # [Cout, Cin, 3, 3] -> [Cout, (kh, kw, Cin)]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+class VaeDecoderEngine:
+    """Drop-in for `pipe.vae` on the decode side: `.decode(z).sample`, `.config.scaling_factor`,
+    `.config.block_out_channels` (what StableDiffusionControlNetInpaintPipeline reads), plus
+    `decode_latents(latents)` = the pipeline method's tensor part in one call."""
+
+    def __init__(self, cfg: VaeConfig, state_dict, device, backend=None):
+        self.cfg, self.dev = cfg, device
+        self.ops = backend or _cuda_ops
+        self.hdt = self.ops.half_dtype()
+        self.config = types.SimpleNamespace(scaling_factor=cfg.scaling_factor, latent_channels=cfg.z_channels,
+                                            block_out_channels=cfg.block_out_channels)
+        sd = {k[len("first_stage_model."):] if k.startswith("first_stage_model.") else k: v
+              for k, v in state_dict.items()}
+        H, F = self._half, self._f32
+        w = {}
+        # tiny-depth convolutions run on the direct kernels: fp32 weights laid out [kh, kw, Cin, Cout]
+        w["pqc.w"] = F(sd["post_quant_conv.weight"].permute(2, 3, 1, 0))
+        w["pqc.b"] = F(sd["post_quant_conv.bias"])
+        w["cin.w"] = F(sd["decoder.conv_in.weight"].permute(2, 3, 1, 0))
+        w["cin.b"] = F(sd["decoder.conv_in.bias"])
+        self.blocks, last = decoder_blocks(cfg)
+        for kind, p, cin, cout in self.blocks:
+            if kind == "res":
+                for n in ("norm1", "norm2"):
+                    w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = F(sd[f"{p}.{n}.weight"]), F(sd[f"{p}.{n}.bias"])
+                w[p + ".conv1.w"], w[p + ".conv1.b"] = H(_conv3_pack(sd[p + ".conv1.weight"])), F(sd[p + ".conv1.bias"])
+                c2, b2 = _conv3_pack(sd[p + ".conv2.weight"]), sd[p + ".conv2.bias"]
+                if cin != cout:   # nin_shortcut as extra K columns of conv2 (same trick as the UNet ResBlock)
+                    c2 = torch.cat([c2, sd[p + ".nin_shortcut.weight"].reshape(cout, cin)], 1)
+                    b2 = b2 + sd[p + ".nin_shortcut.bias"]
+                w[p + ".conv2.w"], w[p + ".conv2.b"] = H(c2), F(b2)
+            elif kind == "attn":
+                w[p + ".norm.g"], w[p + ".norm.b"] = F(sd[p + ".norm.weight"]), F(sd[p + ".norm.bias"])
+                c = cin
+                qk = torch.cat([sd[p + ".q.weight"].reshape(c, c), sd[p + ".k.weight"].reshape(c, c)], 0)
+                w[p + ".qk.w"], w[p + ".qk.b"] = H(qk), F(torch.cat([sd[p + ".q.bias"], sd[p + ".k.bias"]]))
+                w[p + ".v.w"] = H(sd[p + ".v.weight"].reshape(c, c))
+                # softmax rows sum to 1, so v's bias passes straight through the attention: P (V + 1 b^T) = P V + b^T
+                w[p + ".v.b"] = F(sd[p + ".v.bias"])
+                w[p + ".proj.w"], w[p + ".proj.b"] = H(sd[p + ".proj_out.weight"].reshape(c, c)), F(sd[p + ".proj_out.bias"])
+            else:
+                w[p + ".conv.w"], w[p + ".conv.b"] = H(_conv3_pack(sd[p + ".conv.weight"])), F(sd[p + ".conv.bias"])
+        w["nout.g"], w["nout.b"] = F(sd["decoder.norm_out.weight"]), F(sd["decoder.norm_out.bias"])
+        co = _conv3_pack(sd["decoder.conv_out.weight"])                       # [3, 9*C]
+        self.cout_pad = 8
+        cop = torch.zeros(self.cout_pad, co.shape[1], dtype=co.dtype, device=co.device)
+        cop[:cfg.out_ch] = co
+        bop = torch.zeros(self.cout_pad, dtype=co.dtype, device=co.device)
+        bop[:cfg.out_ch] = sd["decoder.conv_out.bias"]
+        w["cout.w"], w["cout.b"] = H(cop), F(bop)
+        self.last_ch = last
+        self.w = w
+        self._gn_ws = {}
+        self._graphs = {}
+
+    def _half(self, t):
+        return t.detach().to(device=self.dev, dtype=self.hdt).contiguous()
+
+    def _f32(self, t):
+        return t.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+
+    def _new(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.dev, dtype=dtype or self.hdt)
+
+    def weight_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+    # ------------------------------------------------------------------------------------------
+    def _gn(self, x, g, b, B, HW, C_, silu):
+        out = self._new(B * HW, C_)
+        ws = self._gn_ws.get(B)      # zero-initialised once; the kernel leaves it zeroed for the next launch
+        if ws is None:
+            ws = self._gn_ws[B] = torch.zeros(B * (self.cfg.num_groups * 2 + 2), device=self.dev, dtype=torch.float32)
+        self.ops.groupnorm(x, g, b, out, B=B, HW=HW, C_=C_, groups=self.cfg.num_groups, eps=self.cfg.eps,
+                           silu=silu, workspace=ws)
+        return out
+
+    def _res(self, p, x, B, H, W_, cin, cout):
+        o, w = self.ops, self.w
+        a1 = self._gn(x, w[p + ".norm1.g"], w[p + ".norm1.b"], B, H * W_, cin, True)
+        h1 = self._new(B * H * W_, cout)
+        o.gemm(a1, w[p + ".conv1.w"], h1, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cin), bias=w[p + ".conv1.b"])
+        a2 = self._gn(h1, w[p + ".norm2.g"], w[p + ".norm2.b"], B, H * W_, cout, True)
+        out = self._new(B * H * W_, cout)
+        if cin != cout:
+            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout),
+                   a_extra=x.view(B, H, W_, cin), ld_extra=cin, bias=w[p + ".conv2.b"])
+        else:
+            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout),
+                   bias=w[p + ".conv2.b"], residual=x)
+        return out
+
+    def _attn(self, p, x, B, H, W_, c):
+        o, w = self.ops, self.w
+        N = H * W_
+        hn = self._gn(x, w[p + ".norm.g"], w[p + ".norm.b"], B, N, c, False)
+        qk = self._new(B * N, 2 * c)
+        o.gemm(hn, w[p + ".qk.w"], qk, bias=w[p + ".qk.b"])
+        out = self._new(B * N, c)
+        s = self._new(N, N, dtype=torch.float32)
+        pr = self._new(N, N)
+        vt = self._new(c, N)
+        ao = self._new(N, c)
+        for b in range(B):                                   # one head per image: plain GEMMs
+            rows = slice(b * N, (b + 1) * N)
+            o.gemm(qk[rows, :c], qk[rows, c:], out_f32=s, K=c, lda=2 * c, ldw=2 * c, out_scale=float(c) ** -0.5)
+            o.softmax_rows(s, pr, rows=N, cols=N)
+            o.gemm(w[p + ".v.w"], hn[rows], vt)                                  # V^T = Wv hn^T   [c, N]
+            o.gemm(pr, vt, ao, bias=w[p + ".v.b"])                               # P V + b_v
+            o.gemm(ao, w[p + ".proj.w"], out[rows], bias=w[p + ".proj.b"], residual=x[rows])
+        return out
+
+    def decode(self, z):
+        """z: [B, z_channels, h, w] (already divided by scaling_factor) -> object with
+        `.sample` = fp32 [B, 3, 8h, 8w] in the decoder's native range (about [-1, 1])."""
+        return types.SimpleNamespace(sample=self._decode(z, post=False))
+
+    def decode_latents(self, latents, use_graph=True):
+        """latents as the denoising loop leaves them -> fp32 [B, 3, 8h, 8w] in [0, 1]
+        (decode_latents up to the .cpu().permute().numpy() plumbing).  On the CUDA backend the ~170
+        launches are captured once per latent shape into a CUDA graph and replayed."""
+        if not use_graph or self.ops is not _cuda_ops:
+            return self._decode(latents.float() / self.cfg.scaling_factor, post=True)
+        key = tuple(latents.shape)
+        st = self._graphs.get(key)
+        if st is None:
+            static_in = torch.zeros(key, device=self.dev, dtype=torch.float32)
+            static_in.copy_(latents)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._decode(static_in / self.cfg.scaling_factor, post=True)      # warm-up: allocator, func attributes
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._decode(static_in / self.cfg.scaling_factor, post=True)
+            st = self._graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = st
+        static_in.copy_(latents, non_blocking=True)
+        g.replay()
+        return static_out.clone()
+
+    def _decode(self, z, post):
+        o, w, cfg = self.ops, self.w, self.cfg
+        B, zc, H, W_ = z.shape
+        if zc != cfg.z_channels:
+            raise ValueError(f"expected {cfg.z_channels} latent channels, got {zc}")
+        zh = z.to(self.dev).permute(0, 2, 3, 1).contiguous().to(self.hdt)          # NHWC half [B,h,w,4]
+        y = self._new(B * H * W_, cfg.z_channels)
+        o.conv_direct(zh, w["pqc.w"], w["pqc.b"], y, B=B, Hin=H, Win=W_, Cin=cfg.embed_dim, Cout=cfg.z_channels,
+                      ksize=1)
+        top = cfg.ch * cfg.ch_mult[-1]
+        h = self._new(B * H * W_, top)
+        o.conv_direct(y, w["cin.w"], w["cin.b"], h, B=B, Hin=H, Win=W_, Cin=cfg.z_channels, Cout=top, ksize=3)
+        for kind, p, cin, cout in self.blocks:
+            if kind == "res":
+                h = self._res(p, h, B, H, W_, cin, cout)
+            elif kind == "attn":
+                h = self._attn(p, h, B, H, W_, cin)
+            else:
+                up = self._new(B * 4 * H * W_, cin)
+                o.upsample2x(h, up, B=B, H=H, W=W_, C_=cin)
+                H, W_ = 2 * H, 2 * W_
+                h = self._new(B * H * W_, cin)
+                o.gemm(up, w[p + ".conv.w"], h, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cin), bias=w[p + ".conv.b"])
+        a = self._gn(h, w["nout.g"], w["nout.b"], B, H * W_, self.last_ch, True)
+        y8 = self._new(B * H * W_, self.cout_pad)
+        o.gemm(a, w["cout.w"], y8, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, self.last_ch), bias=w["cout.b"])
+        img = torch.empty(B, cfg.out_ch, H, W_, device=self.dev, dtype=torch.float32)
+        if post:
+            o.image_out(y8, img, B=B, HW=H * W_, C_=cfg.out_ch, ldx=self.cout_pad, scale=0.5, shift=0.5, lo=0.0, hi=1.0)
+        else:
+            o.image_out(y8, img, B=B, HW=H * W_, C_=cfg.out_ch, ldx=self.cout_pad, scale=1.0, shift=0.0,
+                        lo=-3.0e38, hi=3.0e38)
+        return img

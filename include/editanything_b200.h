@@ -225,6 +225,19 @@ int ea_sam_patchify(const float* img, void* out, int B, int Cin, int H, int W, i
                     void* stream);
 int ea_nhwc_to_nchw_f32(const void* x, float* out, int B, int HW, int C, void* stream);
 
+/* ---- VAE decoder helpers (reference ldm/modules/diffusionmodules/model.py) ----
+ * ea_softmax_rows: p[r, :] = softmax(s[r, :]) for fp32 logits [rows, cols] (row stride lds) -> half
+ *   [rows, cols] (row stride ldp); cols % 4 == 0.  The VAE AttnBlock (model.py:181-210) is single-head
+ *   with d = C = 512: its logits come from ea_gemm (fp32 output, scale C^-0.5 in the epilogue), this
+ *   kernel normalises them, a second ea_gemm applies them to V.
+ * ea_image_out: half NHWC rows of width ldx (first C channels used) -> fp32 NCHW [B, C, HW],
+ *   out = clamp(x * scale + shift, lo, hi): decode_latents' (image / 2 + 0.5).clamp(0, 1)
+ *   (utils/stable_diffusion_controlnet_inpaint.py:718-724) fused with the layout change. */
+int ea_softmax_rows(const float* s, long long lds, void* p, long long ldp, int rows, int cols,
+                    void* stream);
+int ea_image_out(const void* x, long long ldx, float* out, int B, long long HW, int C, float scale,
+                 float shift, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,13 +116,14 @@ def layernorm(x, gamma, beta, out, *, M, C_, eps=1e-5, ldx=None, ldo=None):
 
 def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, silu=False, add=None, ldo=0):
     _bump()
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, stride=stride, padding=ksize // 2)
+    y = F.conv2d(x.float().reshape(B, Hin, Win, Cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, stride=stride,
+                 padding=ksize // 2)
     if silu:
         y = F.silu(y)
     y = y.permute(0, 2, 3, 1)
     if add is not None:
-        y = y + add.float()
-    out.copy_(y)
+        y = y + add.float().reshape(y.shape)
+    out.copy_(y.reshape(out.shape))
     return out
 
 
@@ -139,7 +140,8 @@ def conv_in(x, w, bias, out, *, B, H, W, Cin, Cout, out2=None, add=None, ldo=0, 
 
 def upsample2x(x, out, *, B, H, W, C_):
     _bump()
-    out.copy_(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1))
+    out.copy_(F.interpolate(x.float().reshape(B, H, W, C_).permute(0, 3, 1, 2), scale_factor=2,
+                            mode="nearest").permute(0, 2, 3, 1).reshape(out.shape))
     return out
 
 
@@ -218,3 +220,17 @@ def nhwc_to_nchw_f32(x, out, *, B, HW, C_):
     _bump()
     out.copy_(x.float().reshape(B, HW, C_).permute(0, 2, 1).reshape(out.shape))
     return out
+
+
+def softmax_rows(s, p, *, rows, cols, lds=None, ldp=None):
+    _bump()
+    p.copy_(s.float().reshape(rows, cols).softmax(-1).reshape(p.shape))
+    return p
+
+
+def image_out(x, out, *, B, HW, C_, ldx, scale=0.5, shift=0.5, lo=0.0, hi=1.0):
+    _bump()
+    v = x.float().reshape(B, HW, ldx)[:, :, :C_] * scale + shift
+    out.copy_(v.clamp(lo, hi).permute(0, 2, 1).reshape(out.shape))
+    return out
+
