@@ -319,9 +319,14 @@ class StableDiffusionControlNetInpaintPipeline:
         return lat
 
     def decode_latents(self, latents):
-        """utils/...inpaint.py:718-724."""
-        image = self.vae.decode(latents / self.vae.config.scaling_factor).sample
-        image = (image / 2 + 0.5).clamp(0, 1)
+        """utils/...inpaint.py:718-724.  A `VaeDecoderEngine` (editanything_b200.vae) does the 1/scaling_factor,
+        the decode and the (x / 2 + 0.5).clamp(0, 1) in its own kernels; any other object with the diffusers
+        AutoencoderKL surface goes through the reference's three lines."""
+        if hasattr(self.vae, "decode_latents"):
+            image = self.vae.decode_latents(latents)
+        else:
+            image = self.vae.decode(latents / self.vae.config.scaling_factor).sample
+            image = (image / 2 + 0.5).clamp(0, 1)
         return image.cpu().permute(0, 2, 3, 1).float().numpy()
 
     @staticmethod

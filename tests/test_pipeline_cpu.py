@@ -159,3 +159,32 @@ def test_preparation_helpers():
     s = DDIMScheduler()
     s.set_timesteps(30)
     assert len(s.timesteps) == 31 and int(s.timesteps[0]) == 991    # reference quirk: S=30 -> 31 steps
+
+
+def test_decode_through_the_vae_engine():
+    """output_type='np' with editanything_b200.vae.VaeDecoderEngine attached as `pipe.vae` == the oracle's
+    decode_latents (utils/...inpaint.py:718-724) of the latents the same call returns with output_type='latent'."""
+    from editanything_b200.vae import VAE_TINY, VaeDecoderEngine, make_vae_state_dict
+    from oracle import vae_oracle as V
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup(n_cn=1)
+    vsd = make_vae_state_dict(VAE_TINY, 77)
+    kw = dict(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+              num_inference_steps=4, guidance_scale=7.0, prompt_embeds=pe, negative_prompt_embeds=ne,
+              controlnet_conditioning_scale=1.0, num_images_per_prompt=1, latents=torch.randn(1, 4, 8, 8, generator=torch.manual_seed(3)))
+    lat = pipe(output_type="latent", **kw).images
+    pipe.vae = _EncDec(VaeDecoderEngine(VAE_TINY, vsd, torch.device("cpu"), backend=cpu_ops))
+    out = pipe(output_type="np", **kw).images
+    with torch.no_grad():
+        ref = V.decode_latents(lat.float(), vsd, VAE_TINY).permute(0, 2, 3, 1).numpy()
+    # the VAE_TINY decoder has one upsampling level: 8x8 latents -> 16x16 image
+    assert out.shape == ref.shape == (1, 16, 16, 3)
+    assert abs(out - ref).max() < 1e-3
+
+
+class _EncDec:
+    """The decoder engine plus FakeVAE's encode (the encode side stays PyTorch)."""
+
+    def __init__(self, dec):
+        self._dec, self.config = dec, dec.config
+        self.decode_latents, self.decode, self.encode = dec.decode_latents, dec.decode, FakeVAE().encode
+
