@@ -384,7 +384,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
-    if (p.mode == EA_GEMM_CONV_S2) {
+    if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmA3);
@@ -469,9 +469,14 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else if (p.mode == EA_GEMM_CONV_S1) {
             tma_load_4d(sa, &tmA0, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, n0);
           } else {
-            // stride 2: input row 2*oh + kh - 1 lives in phase ph = (kh != 1) at index oh + dh
-            const int ph = (kh == 1) ? 0 : 1, dh = (kh == 0) ? -1 : 0;
-            const int pw = (kw == 1) ? 0 : 1, dw = (kw == 0) ? -1 : 0;
+            // stride 2, pad 1: input row 2*oh + kh - 1 lives in phase ph = (kh != 1) at index oh + dh.
+            // stride 2, pad (0,1,0,1) (CONV_S2A, the VAE encoder's Downsample): input row 2*oh + kh lives in
+            // phase ph = (kh == 1) at index oh + (kh == 2); the bottom / right padding is TMA zero fill.
+            const bool asym = p.mode == EA_GEMM_CONV_S2A;
+            const int ph = asym ? (kh == 1 ? 1 : 0) : (kh == 1 ? 0 : 1);
+            const int dh = asym ? (kh == 2 ? 1 : 0) : (kh == 0 ? -1 : 0);
+            const int pw = asym ? (kw == 1 ? 1 : 0) : (kw == 1 ? 0 : 1);
+            const int dw = asym ? (kw == 2 ? 1 : 0) : (kw == 0 ? -1 : 0);
             const int sel = ph * 2 + pw;
             const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
             tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
@@ -732,13 +737,16 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int u1 = take_all ? units : (int)(((long long)units * (blockIdx.z + 1)) / p.splits);
       // Stage 1 (all 128 threads, float4 granularity, loads of the sibling partials unrolled for
       // memory-level parallelism) sums this CTA's share into the now-idle pipeline smem; stage 2
-      // runs the fused epilogue on whole 32-column units.  Pieces of <= 64 units (<= 17 KB).
+      // runs the fused epilogue on whole 32-column units.  Pieces of <= 128 units (<= 35 KB, the pipeline
+      // stages hold >= 36 KB): every epilogue thread owns one unit in stage 2 (pieces of 64 left half of
+      // them idle and needed twice as many serialized piece rounds: the fix-up of a 128-wide, 3-way split
+      // tile took 20 us, profiles/r01p_exp_step_chain_gemm_in_context.txt).
       const int segs = geglu ? 2 : 1;                 // 32-float segments per unit (value | gate)
       const int ustride = segs * 32 + 4;              // padded floats per unit in smem
       float* stage = reinterpret_cast<float*>(smem);
       const size_t split_stride = (size_t)BM * p.BN;
-      for (int ub = u0; ub < u1; ub += 64) {
-        const int nu = min(64, u1 - ub);
+      for (int ub = u0; ub < u1; ub += 128) {
+        const int nu = min(128, u1 - ub);
         const int nvec4 = nu * segs * 8;
         for (int idx = et; idx < nvec4; idx += 128) {
           const int ul = idx / (segs * 8);
@@ -1035,7 +1043,7 @@ extern "C" int ea_gemm_plan(int m_tiles, int N, int k_blocks, int act, long long
 extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->a || !a->w || (!a->out && !a->out_f32)) return EA_ERR_ARG;
-  if (a->mode < 0 || a->mode > 2) return EA_ERR_ARG;
+  if (a->mode < 0 || a->mode > EA_GEMM_CONV_S2A) return EA_ERR_ARG;
   if (a->N <= 0 || a->M <= 0) return EA_ERR_ARG;
   if (a->N % 8 != 0) return EA_ERR_SHAPE;
 
@@ -1129,7 +1137,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   const long long ws_floats =
       (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
   static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
-  const bool can_two = a->mode != EA_GEMM_CONV_S2 && two_env != 0 && a->force_2cta >= 0;
+  const bool can_two = a->mode != EA_GEMM_CONV_S2 && a->mode != EA_GEMM_CONV_S2A && two_env != 0 && a->force_2cta >= 0;
   GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
   if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
     plan.two = 1; plan.splits = 1; plan.kbps = nkb;

@@ -9,6 +9,11 @@ Reference semantics followed (paths relative to the reference root):
                                                      -> conv3x3, + x (or + nin_shortcut 1x1 (x))
     AttnBlock.forward             model.py:181-210   GN -> q, k, v 1x1 -> softmax(q k^T C^-1/2) v -> proj, + x
     Upsample.forward              model.py:60-64     nearest x2 -> conv3x3
+and, for the encode side (`prepare_masked_image_latents`, utils/...inpaint.py:1056-1105 -> vae.encode):
+    AutoencoderKL.encode          ldm/models/autoencoder.py:82-86      Encoder -> quant_conv (1x1) -> moments
+    Encoder.forward               model.py:519-543
+    Downsample.forward            model.py:79-86     F.pad(x, (0,1,0,1)) -> conv3x3 stride 2 pad 0 (ea_gemm CONV_S2A)
+    DiagonalGaussianDistribution  ldm/modules/distributions/distributions.py:24-45  mean, logvar.clamp(-30, 20)
 Execution: channels-last half activations, fp32 accumulation; every 3x3 convolution is the tcgen05
 implicit GEMM (ea_gemm CONV_S1), the 1x1 shortcut of a channel-changing ResnetBlock rides along as extra
 K columns of conv2, GroupNorm + swish is one fused launch, and the single-head d = 512 attention is two
@@ -22,35 +27,29 @@ import torch
 
 from . import _lib as L
 from . import ops as _cuda_ops
-from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, make_vae_state_dict  # noqa: F401
+from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, encoder_blocks, make_vae_state_dict  # noqa: F401
 
 
 def _conv3_pack(w):  # [Cout, Cin, 3, 3] -> [Cout, (kh, kw, Cin)]
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-class VaeDecoderEngine:
-    """Drop-in for `pipe.vae` on the decode side: `.decode(z).sample`, `.config.scaling_factor`,
-    `.config.block_out_channels` (what StableDiffusionControlNetInpaintPipeline reads), plus
-    `decode_latents(latents)` = the pipeline method's tensor part in one call."""
+class _VaeBase:
+    """Weight packing and the ResnetBlock / AttnBlock executors shared by the two halves."""
 
-    def __init__(self, cfg: VaeConfig, state_dict, device, backend=None):
+    def _setup(self, cfg, device, backend):
         self.cfg, self.dev = cfg, device
         self.ops = backend or _cuda_ops
         self.hdt = self.ops.half_dtype()
         self.config = types.SimpleNamespace(scaling_factor=cfg.scaling_factor, latent_channels=cfg.z_channels,
                                             block_out_channels=cfg.block_out_channels)
-        sd = {k[len("first_stage_model."):] if k.startswith("first_stage_model.") else k: v
-              for k, v in state_dict.items()}
-        H, F = self._half, self._f32
-        w = {}
-        # tiny-depth convolutions run on the direct kernels: fp32 weights laid out [kh, kw, Cin, Cout]
-        w["pqc.w"] = F(sd["post_quant_conv.weight"].permute(2, 3, 1, 0))
-        w["pqc.b"] = F(sd["post_quant_conv.bias"])
-        w["cin.w"] = F(sd["decoder.conv_in.weight"].permute(2, 3, 1, 0))
-        w["cin.b"] = F(sd["decoder.conv_in.bias"])
-        self.blocks, last = decoder_blocks(cfg)
-        for kind, p, cin, cout in self.blocks:
+        self.w = {}
+        self._gn_ws = {}
+        self._graphs = {}
+
+    def _pack_blocks(self, sd, blocks):
+        H, F, w = self._half, self._f32, self.w
+        for kind, p, cin, cout in blocks:
             if kind == "res":
                 for n in ("norm1", "norm2"):
                     w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = F(sd[f"{p}.{n}.weight"]), F(sd[f"{p}.{n}.bias"])
@@ -69,20 +68,28 @@ class VaeDecoderEngine:
                 # softmax rows sum to 1, so v's bias passes straight through the attention: P (V + 1 b^T) = P V + b^T
                 w[p + ".v.b"] = F(sd[p + ".v.bias"])
                 w[p + ".proj.w"], w[p + ".proj.b"] = H(sd[p + ".proj_out.weight"].reshape(c, c)), F(sd[p + ".proj_out.bias"])
-            else:
+            else:   # upsample.conv / downsample.conv
                 w[p + ".conv.w"], w[p + ".conv.b"] = H(_conv3_pack(sd[p + ".conv.weight"])), F(sd[p + ".conv.bias"])
-        w["nout.g"], w["nout.b"] = F(sd["decoder.norm_out.weight"]), F(sd["decoder.norm_out.bias"])
-        co = _conv3_pack(sd["decoder.conv_out.weight"])                       # [3, 9*C]
-        self.cout_pad = 8
-        cop = torch.zeros(self.cout_pad, co.shape[1], dtype=co.dtype, device=co.device)
-        cop[:cfg.out_ch] = co
-        bop = torch.zeros(self.cout_pad, dtype=co.dtype, device=co.device)
-        bop[:cfg.out_ch] = sd["decoder.conv_out.bias"]
-        w["cout.w"], w["cout.b"] = H(cop), F(bop)
-        self.last_ch = last
-        self.w = w
-        self._gn_ws = {}
-        self._graphs = {}
+
+    def _graphed(self, key, x, fn):
+        """Run fn(static copy of x) through a CUDA graph captured once per `key` (CUDA backend only)."""
+        st = self._graphs.get(key)
+        if st is None:
+            static_in = torch.zeros(tuple(x.shape), device=self.dev, dtype=torch.float32)
+            static_in.copy_(x)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn(static_in)                                      # warm-up: allocator, function attributes
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = fn(static_in)
+            st = self._graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = st
+        static_in.copy_(x, non_blocking=True)
+        g.replay()
+        return static_out.clone()
 
     def _half(self, t):
         return t.detach().to(device=self.dev, dtype=self.hdt).contiguous()
@@ -141,6 +148,34 @@ class VaeDecoderEngine:
             o.gemm(ao, w[p + ".proj.w"], out[rows], bias=w[p + ".proj.b"], residual=x[rows])
         return out
 
+
+class VaeDecoderEngine(_VaeBase):
+    """Drop-in for `pipe.vae` on the decode side: `.decode(z).sample`, `.config.scaling_factor`,
+    `.config.block_out_channels` (what StableDiffusionControlNetInpaintPipeline reads), plus
+    `decode_latents(latents)` = the pipeline method's tensor part in one call."""
+
+    def __init__(self, cfg: VaeConfig, state_dict, device, backend=None):
+        self._setup(cfg, device, backend)
+        sd = {k[len("first_stage_model."):] if k.startswith("first_stage_model.") else k: v
+              for k, v in state_dict.items()}
+        H, F, w = self._half, self._f32, self.w
+        # tiny-depth convolutions run on the direct kernels: fp32 weights laid out [kh, kw, Cin, Cout]
+        w["pqc.w"] = F(sd["post_quant_conv.weight"].permute(2, 3, 1, 0))
+        w["pqc.b"] = F(sd["post_quant_conv.bias"])
+        w["cin.w"] = F(sd["decoder.conv_in.weight"].permute(2, 3, 1, 0))
+        w["cin.b"] = F(sd["decoder.conv_in.bias"])
+        self.blocks, last = decoder_blocks(cfg)
+        self._pack_blocks(sd, self.blocks)
+        w["nout.g"], w["nout.b"] = F(sd["decoder.norm_out.weight"]), F(sd["decoder.norm_out.bias"])
+        co = _conv3_pack(sd["decoder.conv_out.weight"])                       # [3, 9*C]
+        self.cout_pad = 8
+        cop = torch.zeros(self.cout_pad, co.shape[1], dtype=co.dtype, device=co.device)
+        cop[:cfg.out_ch] = co
+        bop = torch.zeros(self.cout_pad, dtype=co.dtype, device=co.device)
+        bop[:cfg.out_ch] = sd["decoder.conv_out.bias"]
+        w["cout.w"], w["cout.b"] = H(cop), F(bop)
+        self.last_ch = last
+
     def decode(self, z):
         """z: [B, z_channels, h, w] (already divided by scaling_factor) -> object with
         `.sample` = fp32 [B, 3, 8h, 8w] in the decoder's native range (about [-1, 1])."""
@@ -152,24 +187,8 @@ class VaeDecoderEngine:
         launches are captured once per latent shape into a CUDA graph and replayed."""
         if not use_graph or self.ops is not _cuda_ops:
             return self._decode(latents.float() / self.cfg.scaling_factor, post=True)
-        key = tuple(latents.shape)
-        st = self._graphs.get(key)
-        if st is None:
-            static_in = torch.zeros(key, device=self.dev, dtype=torch.float32)
-            static_in.copy_(latents)
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                self._decode(static_in / self.cfg.scaling_factor, post=True)      # warm-up: allocator, func attributes
-            torch.cuda.current_stream().wait_stream(s)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                static_out = self._decode(static_in / self.cfg.scaling_factor, post=True)
-            st = self._graphs[key] = (g, static_in, static_out)
-        g, static_in, static_out = st
-        static_in.copy_(latents, non_blocking=True)
-        g.replay()
-        return static_out.clone()
+        return self._graphed(("dec",) + tuple(latents.shape), latents,
+                             lambda x: self._decode(x / self.cfg.scaling_factor, post=True))
 
     def _decode(self, z, post):
         o, w, cfg = self.ops, self.w, self.cfg
@@ -204,3 +223,99 @@ class VaeDecoderEngine:
             o.image_out(y8, img, B=B, HW=H * W_, C_=cfg.out_ch, ldx=self.cout_pad, scale=1.0, shift=0.0,
                         lo=-3.0e38, hi=3.0e38)
         return img
+
+
+class DiagonalGaussian:
+    """`vae.encode(x).latent_dist` (ldm/modules/distributions/distributions.py:24-45; diffusers'
+    DiagonalGaussianDistribution has the same arithmetic): moments [B, 2z, h, w] -> mean | logvar."""
+
+    def __init__(self, moments):
+        self.mean, logvar = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None):
+        # plumbing on a [B, z, h, w] tensor; noise drawn on the generator's device like diffusers' randn_tensor
+        gdev = generator.device if generator is not None else self.mean.device
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.mean.dtype)
+        return self.mean + self.std * noise.to(self.mean.device)
+
+    def mode(self):
+        return self.mean
+
+
+class VaeEncoderEngine(_VaeBase):
+    """Encode side of `pipe.vae`: `.encode(x).latent_dist.sample(generator)` with x the [-1, 1] image
+    [B, 3, H, W] (prepare_masked_image_latents, utils/...inpaint.py:1056-1105; the caller multiplies the
+    sample by `config.scaling_factor`)."""
+
+    def __init__(self, cfg: VaeConfig, state_dict, device, backend=None):
+        self._setup(cfg, device, backend)
+        sd = {k[len("first_stage_model."):] if k.startswith("first_stage_model.") else k: v
+              for k, v in state_dict.items()}
+        H, F, w = self._half, self._f32, self.w
+        ci = sd["encoder.conv_in.weight"]                                    # [ch, 3, 3, 3]
+        self.in_ch = ci.shape[1]
+        cip = torch.zeros(ci.shape[0], 4, 3, 3, dtype=ci.dtype, device=ci.device)   # image padded to 4 channels
+        cip[:, :self.in_ch] = ci
+        w["cin.w"], w["cin.b"] = F(cip.permute(2, 3, 1, 0)), F(sd["encoder.conv_in.bias"])
+        self.blocks, last = encoder_blocks(cfg)
+        self._pack_blocks(sd, self.blocks)
+        w["nout.g"], w["nout.b"] = F(sd["encoder.norm_out.weight"]), F(sd["encoder.norm_out.bias"])
+        w["cout.w"], w["cout.b"] = H(_conv3_pack(sd["encoder.conv_out.weight"])), F(sd["encoder.conv_out.bias"])
+        w["qc.w"], w["qc.b"] = F(sd["quant_conv.weight"].permute(2, 3, 1, 0)), F(sd["quant_conv.bias"])
+        self.last_ch = last
+        if (2 * cfg.z_channels) % 8 != 0:
+            raise ValueError("2 * z_channels must be a multiple of 8 (GEMM output width)")
+
+    def encode(self, x, use_graph=True):
+        if x.dim() != 4 or x.shape[1] != self.in_ch:
+            raise ValueError(f"expected [B, {self.in_ch}, H, W], got {tuple(x.shape)}")
+        f = 2 ** (self.cfg.num_resolutions - 1)
+        if x.shape[2] % f or x.shape[3] % f:
+            raise ValueError(f"image sides must be multiples of {f}")
+        if use_graph and self.ops is _cuda_ops:
+            m = self._graphed(("enc",) + tuple(x.shape), x, self._moments)
+        else:
+            m = self._moments(x.float())
+        return types.SimpleNamespace(latent_dist=DiagonalGaussian(m))
+
+    def _moments(self, x):
+        """fp32 NCHW image -> fp32 NCHW moments [B, 2z, H/f, W/f] (AutoencoderKL.encode before sampling)."""
+        o, w, cfg = self.ops, self.w, self.cfg
+        B, _, H, W_ = x.shape
+        xh = torch.zeros(B, H, W_, 4, device=self.dev, dtype=self.hdt)
+        xh[..., :self.in_ch] = x.to(self.dev).permute(0, 2, 3, 1)                  # NHWC half, 4th channel zero
+        h = self._new(B * H * W_, cfg.ch)
+        o.conv_in(xh, w["cin.w"], w["cin.b"], h, B=B, H=H, W=W_, Cin=4, Cout=cfg.ch)
+        for kind, p, cin, cout in self.blocks:
+            if kind == "res":
+                h = self._res(p, h, B, H, W_, cin, cout)
+            elif kind == "attn":
+                h = self._attn(p, h, B, H, W_, cin)
+            else:   # Downsample: pad (0,1,0,1), conv3x3 stride 2
+                H, W_ = H // 2, W_ // 2
+                d = self._new(B * H * W_, cin)
+                o.gemm(h, w[p + ".conv.w"], d, mode=L.EA_GEMM_CONV_S2A, conv=(B, H, W_, cin), bias=w[p + ".conv.b"])
+                h = d
+        a = self._gn(h, w["nout.g"], w["nout.b"], B, H * W_, self.last_ch, True)
+        zc2 = 2 * cfg.z_channels
+        m0 = self._new(B * H * W_, zc2)
+        o.gemm(a, w["cout.w"], m0, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, self.last_ch), bias=w["cout.b"])
+        m1 = self._new(B * H * W_, 2 * cfg.embed_dim)
+        o.conv_direct(m0, w["qc.w"], w["qc.b"], m1, B=B, Hin=H, Win=W_, Cin=zc2, Cout=2 * cfg.embed_dim, ksize=1)
+        out = torch.empty(B, 2 * cfg.embed_dim, H, W_, device=self.dev, dtype=torch.float32)
+        o.nhwc_to_nchw_f32(m1, out, B=B, HW=H * W_, C_=2 * cfg.embed_dim)
+        return out
+
+
+class VaeEngine:
+    """Both halves behind the one object the pipeline holds as `pipe.vae` (encode, decode,
+    decode_latents, config)."""
+
+    def __init__(self, cfg: VaeConfig, state_dict, device, backend=None):
+        self.encoder = VaeEncoderEngine(cfg, state_dict, device, backend)
+        self.decoder = VaeDecoderEngine(cfg, state_dict, device, backend)
+        self.config = self.decoder.config
+        self.encode, self.decode, self.decode_latents = self.encoder.encode, self.decoder.decode, self.decoder.decode_latents

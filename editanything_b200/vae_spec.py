@@ -53,14 +53,24 @@ def decoder_blocks(cfg: VaeConfig):
     return out, block_in
 
 
-def vae_decoder_param_shapes(cfg: VaeConfig):
-    """name -> (shape, role); role in {w, b, g (norm scale), nb (norm shift)}."""
-    ps = {"post_quant_conv.weight": ((cfg.z_channels, cfg.embed_dim, 1, 1), "w"),
-          "post_quant_conv.bias": ((cfg.z_channels,), "b")}
-    top = cfg.ch * cfg.ch_mult[-1]
-    ps["decoder.conv_in.weight"] = ((top, cfg.z_channels, 3, 3), "w")
-    ps["decoder.conv_in.bias"] = ((top,), "b")
-    blocks, last = decoder_blocks(cfg)
+def encoder_blocks(cfg: VaeConfig):
+    """[(kind, prefix, cin, cout)] in execution order (Encoder.forward, model.py:519-543): per level
+    num_res_blocks ResnetBlocks and, except at the last level, Downsample; then mid res / attn / res."""
+    out = []
+    block_in = cfg.ch
+    for lvl in range(cfg.num_resolutions):
+        block_out = cfg.ch * cfg.ch_mult[lvl]
+        for i in range(cfg.num_res_blocks):
+            out.append(("res", f"encoder.down.{lvl}.block.{i}", block_in, block_out))
+            block_in = block_out
+        if lvl != cfg.num_resolutions - 1:
+            out.append(("down", f"encoder.down.{lvl}.downsample", block_in, block_in))
+    out += [("res", "encoder.mid.block_1", block_in, block_in), ("attn", "encoder.mid.attn_1", block_in, block_in),
+            ("res", "encoder.mid.block_2", block_in, block_in)]
+    return out, block_in
+
+
+def _block_param_shapes(ps, blocks):
     for kind, p, cin, cout in blocks:
         if kind == "res":
             ps[p + ".norm1.weight"], ps[p + ".norm1.bias"] = ((cin,), "g"), ((cin,), "nb")
@@ -73,20 +83,47 @@ def vae_decoder_param_shapes(cfg: VaeConfig):
             ps[p + ".norm.weight"], ps[p + ".norm.bias"] = ((cin,), "g"), ((cin,), "nb")
             for n in ("q", "k", "v", "proj_out"):
                 ps[f"{p}.{n}.weight"], ps[f"{p}.{n}.bias"] = ((cin, cin, 1, 1), "w"), ((cin,), "b")
-        else:
+        else:   # up: upsample.conv, down: downsample.conv
             ps[p + ".conv.weight"], ps[p + ".conv.bias"] = ((cin, cin, 3, 3), "w"), ((cin,), "b")
+
+
+def vae_encoder_param_shapes(cfg: VaeConfig, in_channels=3):
+    """quant_conv + Encoder (double_z): name -> (shape, role)."""
+    ps = {"encoder.conv_in.weight": ((cfg.ch, in_channels, 3, 3), "w"), "encoder.conv_in.bias": ((cfg.ch,), "b")}
+    blocks, last = encoder_blocks(cfg)
+    _block_param_shapes(ps, blocks)
+    ps["encoder.norm_out.weight"], ps["encoder.norm_out.bias"] = ((last,), "g"), ((last,), "nb")
+    ps["encoder.conv_out.weight"] = ((2 * cfg.z_channels, last, 3, 3), "w")
+    ps["encoder.conv_out.bias"] = ((2 * cfg.z_channels,), "b")
+    ps["quant_conv.weight"] = ((2 * cfg.embed_dim, 2 * cfg.z_channels, 1, 1), "w")
+    ps["quant_conv.bias"] = ((2 * cfg.embed_dim,), "b")
+    return ps
+
+
+def vae_decoder_param_shapes(cfg: VaeConfig):
+    """name -> (shape, role); role in {w, b, g (norm scale), nb (norm shift)}."""
+    ps = {"post_quant_conv.weight": ((cfg.z_channels, cfg.embed_dim, 1, 1), "w"),
+          "post_quant_conv.bias": ((cfg.z_channels,), "b")}
+    top = cfg.ch * cfg.ch_mult[-1]
+    ps["decoder.conv_in.weight"] = ((top, cfg.z_channels, 3, 3), "w")
+    ps["decoder.conv_in.bias"] = ((top,), "b")
+    blocks, last = decoder_blocks(cfg)
+    _block_param_shapes(ps, blocks)
     ps["decoder.norm_out.weight"], ps["decoder.norm_out.bias"] = ((last,), "g"), ((last,), "nb")
     ps["decoder.conv_out.weight"] = ((cfg.out_ch, last, 3, 3), "w")
     ps["decoder.conv_out.bias"] = ((cfg.out_ch,), "b")
     return ps
 
 
-def make_vae_state_dict(cfg: VaeConfig, seed: int, dtype=torch.float32, device="cpu"):
-    """Deterministic synthetic decoder weights (no checkpoint in this environment): conv weights
-    ~ N(0, 1/fan_in), small biases, norm scales around 1 — activations stay O(1) through the stack."""
+def make_vae_state_dict(cfg: VaeConfig, seed: int, dtype=torch.float32, device="cpu", part="decoder"):
+    """Deterministic synthetic weights (no checkpoint in this environment) of the decoder side
+    (`part="decoder"`: post_quant_conv + decoder) or the encoder side (`part="encoder"`: encoder +
+    quant_conv): conv weights ~ N(0, 1/fan_in), small biases, norm scales around 1 — activations stay
+    O(1) through the stack."""
     g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
-    for name, (shape, role) in vae_decoder_param_shapes(cfg).items():
+    shapes = vae_decoder_param_shapes(cfg) if part == "decoder" else vae_encoder_param_shapes(cfg)
+    for name, (shape, role) in shapes.items():
         if role == "w":
             fan_in = 1
             for s in shape[1:]:

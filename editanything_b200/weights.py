@@ -100,51 +100,66 @@ def diffusers_to_ldm(state_dict, kind: str, cfg: UNetConfig):
 
 
 # ---- first-stage decoder (AutoencoderKL) ------------------------------------------------------------
-def vae_ldm_to_diffusers_names(vcfg, attn_style="to_q"):
-    """{ldm parameter name: diffusers AutoencoderKL parameter name} for post_quant_conv + decoder.
-    diffusers numbers the up blocks from the lowest resolution (up_blocks.0 = ldm up.{L-1}), calls the
-    1x1 shortcut `conv_shortcut`, the output norm `conv_norm_out`, and stores the mid attention as Linear
-    layers named to_q/to_k/to_v/to_out.0 (`attn_style="to_q"`, diffusers >= 0.18) or
+def vae_ldm_to_diffusers_names(vcfg, attn_style="to_q", part="decoder"):
+    """{ldm parameter name: diffusers AutoencoderKL parameter name} for post_quant_conv + decoder
+    (`part="decoder"`) or encoder + quant_conv (`part="encoder"`).
+    diffusers numbers the up blocks from the lowest resolution (up_blocks.0 = ldm up.{L-1}; down blocks keep
+    their order), calls the 1x1 shortcut `conv_shortcut`, the output norm `conv_norm_out`, and stores the mid
+    attention as Linear layers named to_q/to_k/to_v/to_out.0 (`attn_style="to_q"`, diffusers >= 0.18) or
     query/key/value/proj_attn (`attn_style="query"`, diffusers <= 0.17, the reference's pin)."""
-    from .vae_spec import vae_decoder_param_shapes
+    from .vae_spec import vae_decoder_param_shapes, vae_encoder_param_shapes
     attn = ({"q": "to_q", "k": "to_k", "v": "to_v", "proj_out": "to_out.0", "norm": "group_norm"} if attn_style == "to_q"
             else {"q": "query", "k": "key", "v": "value", "proj_out": "proj_attn", "norm": "group_norm"})
     L_ = vcfg.num_resolutions
     out = {}
-    for k in vae_decoder_param_shapes(vcfg):
+    shapes = vae_decoder_param_shapes(vcfg) if part == "decoder" else vae_encoder_param_shapes(vcfg)
+    for k in shapes:
         parts = k.split(".")
-        if parts[0] == "post_quant_conv" or parts[1] in ("conv_in", "conv_out"):
+        side = parts[0]                                   # "decoder" | "encoder" | "(post_)quant_conv"
+        if side in ("post_quant_conv", "quant_conv") or parts[1] in ("conv_in", "conv_out"):
             out[k] = k
         elif parts[1] == "norm_out":
-            out[k] = "decoder.conv_norm_out." + parts[-1]
+            out[k] = f"{side}.conv_norm_out." + parts[-1]
         elif parts[1] == "mid":
             if parts[2].startswith("block_"):
                 rest = ".".join(parts[3:]).replace("nin_shortcut", "conv_shortcut")
-                out[k] = f"decoder.mid_block.resnets.{int(parts[2][-1]) - 1}.{rest}"
+                out[k] = f"{side}.mid_block.resnets.{int(parts[2][-1]) - 1}.{rest}"
             else:
-                out[k] = f"decoder.mid_block.attentions.0.{attn[parts[3]]}.{parts[-1]}"
-        else:  # decoder.up.<lvl>.block.<i>.<...> | decoder.up.<lvl>.upsample.conv.<...>
+                out[k] = f"{side}.mid_block.attentions.0.{attn[parts[3]]}.{parts[-1]}"
+        elif parts[1] == "up":   # decoder.up.<lvl>.block.<i>.<...> | decoder.up.<lvl>.upsample.conv.<...>
             ub = L_ - 1 - int(parts[2])
             if parts[3] == "block":
                 rest = ".".join(parts[5:]).replace("nin_shortcut", "conv_shortcut")
                 out[k] = f"decoder.up_blocks.{ub}.resnets.{parts[4]}.{rest}"
             else:
                 out[k] = f"decoder.up_blocks.{ub}.upsamplers.0.conv.{parts[-1]}"
+        else:                    # encoder.down.<lvl>.block.<i>.<...> | encoder.down.<lvl>.downsample.conv.<...>
+            if parts[3] == "block":
+                rest = ".".join(parts[5:]).replace("nin_shortcut", "conv_shortcut")
+                out[k] = f"encoder.down_blocks.{parts[2]}.resnets.{parts[4]}.{rest}"
+            else:
+                out[k] = f"encoder.down_blocks.{parts[2]}.downsamplers.0.conv.{parts[-1]}"
     return out
 
 
-def vae_diffusers_to_ldm(state_dict, vcfg):
-    """Re-key a diffusers AutoencoderKL state dict (either attention spelling; encoder / quant_conv keys
-    ignored) to the ldm names editanything_b200.vae consumes; Linear attention weights become 1x1 convs."""
+def vae_diffusers_to_ldm(state_dict, vcfg, parts=("decoder",)):
+    """Re-key a diffusers AutoencoderKL state dict (either attention spelling) to the ldm names
+    editanything_b200.vae consumes, for the requested parts ("decoder", "encoder"); Linear attention
+    weights become 1x1 convs; keys of the other part are ignored."""
     out = {}
-    for style in ("to_q", "query"):
-        names = vae_ldm_to_diffusers_names(vcfg, style)
-        if all(v in state_dict for v in names.values()):
-            for lk, dk in names.items():
-                t = state_dict[dk]
-                if ".attn_1." in lk and lk.endswith("weight") and ".norm." not in lk and t.dim() == 2:
-                    t = t.reshape(t.shape[0], t.shape[1], 1, 1)
-                out[lk] = t
-            return out
-    missing = [v for v in vae_ldm_to_diffusers_names(vcfg).values() if v not in state_dict][:5]
-    raise KeyError(f"not a diffusers AutoencoderKL decoder state dict; missing e.g. {missing}")
+    for part in parts:
+        done = False
+        for style in ("to_q", "query"):
+            names = vae_ldm_to_diffusers_names(vcfg, style, part)
+            if all(v in state_dict for v in names.values()):
+                for lk, dk in names.items():
+                    t = state_dict[dk]
+                    if ".attn_1." in lk and lk.endswith("weight") and ".norm." not in lk and t.dim() == 2:
+                        t = t.reshape(t.shape[0], t.shape[1], 1, 1)
+                    out[lk] = t
+                done = True
+                break
+        if not done:
+            missing = [v for v in vae_ldm_to_diffusers_names(vcfg, "to_q", part).values() if v not in state_dict][:5]
+            raise KeyError(f"not a diffusers AutoencoderKL {part} state dict; missing e.g. {missing}")
+    return out

@@ -34,7 +34,7 @@ enum ea_status {
   EA_ERR_NODRIVER = -5
 };
 
-enum ea_gemm_mode { EA_GEMM_LINEAR = 0, EA_GEMM_CONV_S1 = 1, EA_GEMM_CONV_S2 = 2 };
+enum ea_gemm_mode { EA_GEMM_LINEAR = 0, EA_GEMM_CONV_S1 = 1, EA_GEMM_CONV_S2 = 2, EA_GEMM_CONV_S2A = 3 };
 enum ea_act { EA_ACT_NONE = 0, EA_ACT_SILU = 1, EA_ACT_GELU = 2, EA_ACT_GEGLU = 3 };
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -64,6 +64,8 @@ void ea_reset_launch_count(void);
  *               a_extra (optional): NHWC [Bsz,H,W,Cin_extra] raw block input whose 1x1
  *               skip-connection conv is folded in as extra K columns (openaimodel.py:233-240).
  * mode CONV_S2: A is NHWC [Bsz, 2H, 2W, Cin]; H, W are the OUTPUT size.
+ * mode CONV_S2A: as CONV_S2 but padded (0,1,0,1) instead of 1 all round - the VAE encoder's Downsample
+ *   (ldm/modules/diffusionmodules/model.py:79-86: F.pad(x, (0,1,0,1)) then a stride-2 pad-0 conv).
  * Epilogue order: +bias[n] -> +rowvec[batch(m), n] -> act -> *out_scale -> +residual[m,n]
  *                 -> (+= out[m,n] if accumulate) -> store out (and out2).
  * act GEGLU: W rows must be pre-interleaved per 128-row block as [64 value rows | 64 gate rows];

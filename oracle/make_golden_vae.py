@@ -41,8 +41,33 @@ def run_case(name, spec):
           "fraction clamped", float(((raw / 2 + 0.5) < 0).float().mean() + ((raw / 2 + 0.5) > 1).float().mean()))
 
 
+ENC_CASES = {"vae_enc_tiny": (VAE_TINY, 2, 32, 411, 17)}     # name -> (cfg, batch, image side, weight seed, image seed)
+ENC_FULL_CASES = {"vae_enc_sd": (SD_VAE, 1, 512, 412, 18)}
+
+
+def make_image(B, side, seed):
+    """A masked source image as prepare_masked_image_latents sees it: [-1, 1] pixels, a masked block zeroed."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, 3, side, side, generator=g) * 2 - 1
+    img[:, :, side // 4:side // 2, side // 4:side // 2] = 0.0
+    return img
+
+
+def run_enc_case(name, spec):
+    cfg, B, side, wseed, iseed = spec
+    sd = make_vae_state_dict(cfg, wseed, part="encoder")
+    m = V.reference_encoder(cfg, sd)(make_image(B, side, iseed))
+    rec = {"meta": dict(name=name, B=B, side=side, weight_seed=wseed, image_seed=iseed,
+                        generator="reference ldm Encoder + quant_conv"), "moments": m.clone()}
+    torch.save(rec, os.path.join(GOLD, name + ".pt"))
+    print(name, tuple(m.shape), "mean abs max", float(m[:, :m.shape[1] // 2].abs().max()), "logvar range",
+          float(m[:, m.shape[1] // 2:].min()), float(m[:, m.shape[1] // 2:].max()))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     for n, s in (FULL_CASES if "--full" in sys.argv else CASES).items():
         run_case(n, s)
+    for n, s in (ENC_FULL_CASES if "--full" in sys.argv else ENC_CASES).items():
+        run_enc_case(n, s)

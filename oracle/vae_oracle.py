@@ -97,3 +97,46 @@ def reference_decoder(cfg: VaeConfig, sd):
         with torch.no_grad():
             return dec(pqc(z))
     return run
+
+
+# ---- encode side -----------------------------------------------------------------------------------
+def downsample(x, sd, p):
+    """Downsample.forward with_conv (model.py:79-86): asymmetric pad (0,1,0,1), stride-2 pad-0 conv."""
+    x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    return F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], stride=2, padding=0)
+
+
+def encode_moments(x, sd, cfg: VaeConfig):
+    """AutoencoderKL.encode up to the distribution (autoencoder.py:82-86): quant_conv(Encoder(x))
+    (Encoder.forward model.py:519-543)."""
+    from editanything_b200.vae_spec import encoder_blocks
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    blocks, _ = encoder_blocks(cfg)
+    for kind, p, cin, cout in blocks:
+        if kind == "res":
+            h = resnet_block(h, sd, p, cfg)
+        elif kind == "attn":
+            h = attn_block(h, sd, p, cfg)
+        else:
+            h = downsample(h, sd, p)
+    h = nonlinearity(normalize(h, sd, "encoder.norm_out", cfg))
+    h = F.conv2d(h, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def reference_encoder(cfg: VaeConfig, sd):
+    """The reference's OWN modules (build container only): ldm Encoder + quant_conv loaded with `sd`."""
+    from oracle import ref_shim
+    ref_shim.load()
+    from ldm.modules.diffusionmodules.model import Encoder
+    enc = Encoder(ch=cfg.ch, out_ch=cfg.out_ch, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks,
+                  attn_resolutions=[], dropout=0.0, in_channels=3, resolution=256, z_channels=cfg.z_channels,
+                  double_z=True, attn_type="vanilla").eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    qc = torch.nn.Conv2d(2 * cfg.z_channels, 2 * cfg.embed_dim, 1)
+    qc.load_state_dict({"weight": sd["quant_conv.weight"], "bias": sd["quant_conv.bias"]})
+
+    def run(x):
+        with torch.no_grad():
+            return qc(enc(x))
+    return run

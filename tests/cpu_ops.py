@@ -8,7 +8,7 @@ editanything_b200.nets against the oracle without a GPU.  It is injected explici
 import torch
 import torch.nn.functional as F
 
-EA_GEMM_LINEAR, EA_GEMM_CONV_S1, EA_GEMM_CONV_S2 = 0, 1, 2
+EA_GEMM_LINEAR, EA_GEMM_CONV_S1, EA_GEMM_CONV_S2, EA_GEMM_CONV_S2A = 0, 1, 2, 3
 EA_ACT_NONE, EA_ACT_SILU, EA_ACT_GELU, EA_ACT_GEGLU = 0, 1, 2, 3
 _count = 0
 
@@ -44,7 +44,10 @@ def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, con
         B, H, W_, Cin = conv
         x = a.float().reshape(B, -1, a.shape[-2] if a.dim() == 4 else (W_ if mode == EA_GEMM_CONV_S1 else 2 * W_), Cin).permute(0, 3, 1, 2)
         wm = w[:, :9 * Cin].float().reshape(Nn, 3, 3, Cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x, wm, stride=1 if mode == EA_GEMM_CONV_S1 else 2, padding=1)
+        if mode == EA_GEMM_CONV_S2A:
+            y = F.conv2d(F.pad(x, (0, 1, 0, 1)), wm, stride=2, padding=0)
+        else:
+            y = F.conv2d(x, wm, stride=1 if mode == EA_GEMM_CONV_S1 else 2, padding=1)
         if a_extra is not None:
             ce = a_extra.shape[-1]
             y = y + F.conv2d(a_extra.float().permute(0, 3, 1, 2), w[:, 9 * Cin:9 * Cin + ce].float().reshape(Nn, ce, 1, 1))
@@ -129,12 +132,12 @@ def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, s
 
 def conv_in(x, w, bias, out, *, B, H, W, Cin, Cout, out2=None, add=None, ldo=0, ldo2=0):
     _bump()
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1)
+    y = F.conv2d(x.float().reshape(B, H, W, Cin).permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1).permute(0, 2, 3, 1)
     if add is not None:
-        y = y + add.float()
-    out.copy_(y)
+        y = y + add.float().reshape(y.shape)
+    out.copy_(y.reshape(out.shape))
     if out2 is not None:
-        out2.copy_(y)
+        out2.copy_(y.reshape(out2.shape))
     return out
 
 
