@@ -228,23 +228,31 @@ def run_ours(args, rank, world, local_rank):
         pass
 
     # ---- first-stage decoder (once per image) -----------------------------------
-    vae_ms, vae = None, None
+    vae_ms, vae_enc_ms, vae = None, None, None
     if not args.no_vae:
-        from editanything_b200.vae import SD_VAE, VaeDecoderEngine, make_vae_state_dict
-        vae = VaeDecoderEngine(SD_VAE, make_vae_state_dict(SD_VAE, 402, device=dev), dev)
+        from editanything_b200.vae import SD_VAE, VaeEngine, make_vae_state_dict
+        vsd = dict(make_vae_state_dict(SD_VAE, 412, device=dev, part="encoder"))
+        vsd.update(make_vae_state_dict(SD_VAE, 402, device=dev))
+        vae = VaeEngine(SD_VAE, vsd, dev)
+        del vsd
         lat = eng.latents().float()
-        for _ in range(2):
-            vae.decode_latents(lat)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(3):
-            vae.decode_latents(lat)
-        s1.record()
-        torch.cuda.synchronize()
-        vae_ms = s0.elapsed_time(s1) / 3
+        src = torch.rand(1, 3, 512, 512, device=dev) * 2 - 1          # the masked source image (prepare_masked_image_latents)
 
-    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0) + (vae_ms or 0.0)
+        def _time(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                fn()
+            s1.record()
+            torch.cuda.synchronize()
+            return s0.elapsed_time(s1) / 3
+        vae_ms = _time(lambda: vae.decode_latents(lat))
+        vae_enc_ms = _time(lambda: vae.encode(src))
+
+    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0) + (vae_ms or 0.0) + (vae_enc_ms or 0.0)
     value = world * 1000.0 / img_ms
 
     # ---- roofline of the dominant kernel (ea_gemm_kernel), live CUDA events ----------------------
@@ -296,12 +304,15 @@ def run_ours(args, rank, world, local_rank):
         hx, hctx = x[:1].pin_memory(), ctx.pin_memory()
         hh = [h.pin_memory() for h in hints]
         himg = torch.randn(1, 3, 1024, 1024).pin_memory() if sam is not None else None
+        hsrc = (torch.rand(1, 3, 512, 512) * 2 - 1).pin_memory() if vae is not None else None
         n_img = 3
 
         def one_image():
             emb = None
             if sam is not None:
                 emb = sam.encode(himg.to(dev, non_blocking=True)).cpu()
+            if vae is not None:      # masked-image latents (utils/...inpaint.py:1056-1105); consumed by the blend
+                vae.encode(hsrc.to(dev, non_blocking=True)).latent_dist.sample()
             eng.prepare(hctx.to(dev, non_blocking=True), [h.to(dev, non_blocking=True) for h in hh], [0.5, 1.0])
             eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
             for i in range(DDIM_STEPS):
@@ -326,14 +337,16 @@ def run_ours(args, rank, world, local_rank):
             dt = t.item()
             allres = gather_sharded(res.to(dev), world, rank, world)   # the single end-of-job collective
             assert allres.shape[0] == world
-        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh) + (himg.numel() if himg is not None else 0)) * 4
+        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh) + (himg.numel() if himg is not None else 0) +
+               (hsrc.numel() if hsrc is not None else 0)) * 4
         d2h = (res.numel() + (emb.numel() if emb is not None else 0)) * 4
         e2e = {"value": round(world * n_img / dt, 4), "unit": "images/s",
                "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": d2h // DDIM_STEPS,
                "ms_per_image": round(dt / n_img * 1e3, 2), "images_timed": n_img,
                "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host ctx / hints / "
-                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> VAE decode -> D2H fp32 image; "
-                       "1 untimed warm-up image; text encoder / SAM mask decoder / VAE encode not included (SURVEY.md 8f)"}
+                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> VAE decode -> D2H fp32 image; pinned "
+                       "host source image -> H2D -> VAE encode; 1 untimed warm-up image; text encoder / SAM mask decoder "
+                       "not included (SURVEY.md 8f)"}
 
     line = {
         "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
@@ -346,8 +359,9 @@ def run_ours(args, rank, world, local_rank):
                    "global_batch": world, "parallelism": f"dp{world} (one image per GPU, final all-gather)",
                    "l2": "weights touched per step (3.16 GB) exceed the 126 MB L2; no explicit flush",
                    "cuda_graph": not args.no_graph, "sam_ms_per_image": sam_ms, "sam": sam_note,
-                   "vae_decode_ms_per_image": vae_ms,
-                   "image": "image_ms = 50 x ms_per_step + SAM encode + VAE decode (kl-f8 decoder, 64x64 -> 512x512)",
+                   "vae_decode_ms_per_image": vae_ms, "vae_encode_ms_per_image": vae_enc_ms,
+                   "image": "image_ms = 50 x ms_per_step + SAM encode + VAE encode of the masked source image "
+                            "(512x512 -> 64x64 latents) + VAE decode (64x64 -> 512x512), kl-f8",
                    "image_ms": round(img_ms, 3), "outputs_finite": finite},
         "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roofline, "e2e": e2e,
@@ -408,13 +422,16 @@ def _oracle_sam_seconds():
 
 
 def _oracle_vae_seconds():
-    """One first-stage decode (latents 64x64 -> 512x512) of the CPU oracle, fp32 (~10-20 s)."""
+    """One first-stage encode (512x512 -> 64x64) + decode (64x64 -> 512x512) of the CPU oracle, fp32 (~15-30 s)."""
     from editanything_b200.vae_spec import SD_VAE, make_vae_state_dict
     from oracle import vae_oracle as V
     sd = make_vae_state_dict(SD_VAE, 402)
+    esd = make_vae_state_dict(SD_VAE, 412, part="encoder")
     lat = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(4)) * SD_VAE.scaling_factor
+    src = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(5)) * 2 - 1
     t0 = time.perf_counter()
     with torch.no_grad():
+        V.encode_moments(src, esd, SD_VAE)
         V.decode_latents(lat, sd, SD_VAE)
     return time.perf_counter() - t0
 
@@ -433,9 +450,9 @@ def cpu_baseline(sample_steps=1):
     vae_s = _oracle_vae_seconds()
     return {"value": round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6), "unit": "images/s", "cores": cores, "kind": "port",
             "ms_per_step": round(dt * 1e3, 1), "sam_ms_per_image": round(sam_s * 1e3, 1),
-            "vae_decode_ms_per_image": round(vae_s * 1e3, 1),
+            "vae_encode_decode_ms_per_image": round(vae_s * 1e3, 1),
             "sample": f"{sample_steps} full-size fused step(s) (2 ControlNets + UNet + CFG + DDIM, B=2, 64x64, fp32) of the "
-                      f"oracle port on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode + 1 VAE decode of the oracle "
+                      f"oracle port on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode + 1 VAE encode + decode of the oracle "
                       f"port; images/s = 1/(50*step + SAM + VAE)"}
 
 
@@ -464,7 +481,7 @@ def run_reference(args, rank, world):
     vae_s = _oracle_vae_seconds()
     v = round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6)
     sample = (f"{k} of the requested {args.steps} steps timed (each a full-size configs[1] fused step on CPU, fp32, "
-              f"{cores} threads; bounded to ~{int(budget_s)} s) + 1 SAM ViT-H encode ({sam_s:.1f} s) + 1 VAE decode "
+              f"{cores} threads; bounded to ~{int(budget_s)} s) + 1 SAM ViT-H encode ({sam_s:.1f} s) + 1 VAE encode + decode "
               f"({vae_s:.1f} s); images/s = 1/(50*step + SAM + VAE)")
     line = {"impl": "reference",
             "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
