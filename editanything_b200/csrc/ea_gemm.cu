@@ -84,7 +84,7 @@ __device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n
 }
 
 // TMEM allocations are powers of two >= 32 columns
-__device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
+__host__ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
   return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
 }
 
@@ -1169,9 +1169,8 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   p.no_spin = a->no_spin;
   if (p.splits > 1) {
     const long long tiles = (long long)m_tiles * n_tiles;
-    if (!ws_floats || tiles > 8192 || tiles * p.splits * (long long)(BM * p.BN) > ws_floats ||
-        tiles * p.splits > 2LL * sm_count())
-      return EA_ERR_SHAPE;  // split CTAs wait for each other: they must all be resident
+    if (!ws_floats || tiles > 8192 || tiles * p.splits * (long long)(BM * p.BN) > ws_floats)
+      return EA_ERR_SHAPE;
     p.cnt = reinterpret_cast<int*>(a->workspace);
     p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + 65536);
   }
@@ -1189,6 +1188,14 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   p.stages = stages;
   p.pair_release = (stages >= 4 && stages % 2 == 0) ? 1 : 0;
   const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * 256 * 4 + 1024;
+  if (p.splits > 1 && !p.no_spin) {
+    // the spinning fix-up makes split CTAs wait for their siblings: every CTA of the grid must be
+    // resident at once, at the occupancy this launch really gets (the planner guarantees it; forced
+    // test configurations are checked here instead of deadlocking)
+    const int tmem_c = tmem_cols_for(p.BN);
+    const int occ = (2 * (smem_bytes + 1024) <= 227 * 1024 && 2 * tmem_c <= 512) ? 2 : 1;
+    if ((long long)m_tiles * n_tiles * p.splits > (long long)occ * sm_count()) return EA_ERR_SHAPE;
+  }
   static int max_set[2] = {0, 0};
   if (smem_bytes > max_set[two]) {
     cudaError_t se = two ? cudaFuncSetAttribute(ea_gemm_kernel<true>,

@@ -67,43 +67,44 @@ def time_cfg(bufs, conv, act, **kw):
     return e0.elapsed_time(e1) * 1e3 / (2 * NL)
 
 
-SHAPES = [
-    ("lin 8192x320 K320 +res", 8192, 320, 320, None, True, 0),
-    ("lin 8192x320 K320", 8192, 320, 320, None, False, 0),
-    ("lin 8192x960 K320 (qkv64)", 8192, 960, 320, None, False, 0),
-    ("lin 8192x320 K1280 +res (ff2_64)", 8192, 320, 1280, None, True, 0),
-    ("geglu 8192x2560 K320", 8192, 2560, 320, None, False, L.EA_ACT_GEGLU),
-    ("lin 2048x640 K640 +res", 2048, 640, 640, None, True, 0),
-    ("lin 2048x1920 K640 (qkv32)", 2048, 1920, 640, None, False, 0),
-    ("lin 2048x640 K2560 +res (ff2_32)", 2048, 640, 2560, None, True, 0),
-    ("geglu 2048x5120 K640", 2048, 5120, 640, None, False, L.EA_ACT_GEGLU),
-    ("lin 512x1280 K1280 +res", 512, 1280, 1280, None, True, 0),
-    ("lin 512x3840 K1280 (qkv16)", 512, 3840, 1280, None, False, 0),
-    ("geglu 512x10240 K1280", 512, 10240, 1280, None, False, L.EA_ACT_GEGLU),
-    ("lin 128x1280 K1280 +res", 128, 1280, 1280, None, True, 0),
-    ("conv64 320->320", 0, 320, 0, (2, 64, 64, 320), False, 0),
-    ("conv32 640->640", 0, 640, 0, (2, 32, 32, 640), False, 0),
-    ("conv16 1280->1280", 0, 1280, 0, (2, 16, 16, 1280), False, 0),
-]
+if __name__ == "__main__":
+    SHAPES = [
+        ("lin 8192x320 K320 +res", 8192, 320, 320, None, True, 0),
+        ("lin 8192x320 K320", 8192, 320, 320, None, False, 0),
+        ("lin 8192x960 K320 (qkv64)", 8192, 960, 320, None, False, 0),
+        ("lin 8192x320 K1280 +res (ff2_64)", 8192, 320, 1280, None, True, 0),
+        ("geglu 8192x2560 K320", 8192, 2560, 320, None, False, L.EA_ACT_GEGLU),
+        ("lin 2048x640 K640 +res", 2048, 640, 640, None, True, 0),
+        ("lin 2048x1920 K640 (qkv32)", 2048, 1920, 640, None, False, 0),
+        ("lin 2048x640 K2560 +res (ff2_32)", 2048, 640, 2560, None, True, 0),
+        ("geglu 2048x5120 K640", 2048, 5120, 640, None, False, L.EA_ACT_GEGLU),
+        ("lin 512x1280 K1280 +res", 512, 1280, 1280, None, True, 0),
+        ("lin 512x3840 K1280 (qkv16)", 512, 3840, 1280, None, False, 0),
+        ("geglu 512x10240 K1280", 512, 10240, 1280, None, False, L.EA_ACT_GEGLU),
+        ("lin 128x1280 K1280 +res", 128, 1280, 1280, None, True, 0),
+        ("conv64 320->320", 0, 320, 0, (2, 64, 64, 320), False, 0),
+        ("conv32 640->640", 0, 640, 0, (2, 32, 32, 640), False, 0),
+        ("conv16 1280->1280", 0, 1280, 0, (2, 16, 16, 1280), False, 0),
+    ]
 
-out = []
-for name, M, N, K, conv, res, act in SHAPES:
-    bufs = make(M, N, K, conv, res, act)
-    auto = time_cfg(bufs, conv, act)
-    rows = []
-    bns = [128] if act == L.EA_ACT_GEGLU else [b for b in (32, 64, 96, 128, 160, 192, 256) if b < N + 32]
-    for bn in bns:
-        for two in (-1, 1):
-            if two == 1 and bn < 64:
-                continue
-            for st in (2, 3, 4, 6, 8):
-                t = time_cfg(bufs, conv, act, force_bn=bn, force_2cta=two, force_stages=st)
-                if t is not None:
-                    rows.append((round(t, 2), bn, two, st))
-    rows.sort()
-    print(f"== {name}: auto {auto:.2f} us; best: " + "  ".join(f"{t}us(bn{bn},two{two},st{st})" for t, bn, two, st in rows[:6]), flush=True)
-    out.append({"name": name, "auto_us": auto, "rows": rows})
-    del bufs
-    torch.cuda.empty_cache()
-if len(sys.argv) > 1:
-    json.dump(out, open(sys.argv[1], "w"))
+    out = []
+    for name, M, N, K, conv, res, act in SHAPES:
+        bufs = make(M, N, K, conv, res, act)
+        auto = time_cfg(bufs, conv, act)
+        rows = []
+        bns = [128] if act == L.EA_ACT_GEGLU else [b for b in (32, 64, 96, 128, 160, 192, 256) if b < N + 32]
+        for bn in bns:
+            for two in (-1, 1):
+                if two == 1 and bn < 64:
+                    continue
+                for st in (2, 3, 4, 6, 8):
+                    t = time_cfg(bufs, conv, act, force_bn=bn, force_2cta=two, force_stages=st)
+                    if t is not None:
+                        rows.append((round(t, 2), bn, two, st))
+        rows.sort()
+        print(f"== {name}: auto {auto:.2f} us; best: " + "  ".join(f"{t}us(bn{bn},two{two},st{st})" for t, bn, two, st in rows[:6]), flush=True)
+        out.append({"name": name, "auto_us": auto, "rows": rows})
+        del bufs
+        torch.cuda.empty_cache()
+    if len(sys.argv) > 1:
+        json.dump(out, open(sys.argv[1], "w"))
