@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p),
         ("act", C.c_int), ("out_scale", C.c_float), ("accumulate", C.c_int),
         ("force_bn", C.c_int), ("force_stages", C.c_int), ("force_splits", C.c_int), ("force_2cta", C.c_int), ("no_spin", C.c_int),
+        ("force_persistent", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
     ]
 

@@ -871,6 +871,293 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
   bn = 128 / (bw * bh);
 }
 
+// ---- persistent variant ---------------------------------------------------------------------------
+// EXPERIMENTAL (off unless ea_gemm_args.force_persistent = 1 or EA_GEMM_PERSIST=1; not yet validated on
+// hardware - DESIGN.md section 8, item 1).  One CTA per SM walks the tile list (tile -> (tm, tn) with tm
+// fastest, so CTAs working side by side share their weight tile in L2) with TWO TMEM accumulators: the
+// epilogue warps drain tile i while the MMA warp already accumulates tile i+1, the TMA ring runs across
+// tile boundaries, and barrier setup / TMEM allocation / the dependency wait are paid once per SM instead
+// of once per tile.  Scope: no CTA pairs, no split-K, half output, epilogue = fast path or GEGLU (the host
+// only selects this kernel when every tile qualifies).
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                          const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmB,
+                          const GemmKParams p, const int num_tiles, const int m_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int a_bytes = BM * BK * 2;
+  const int b_bytes = p.BN * BK * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  // carve: [stages] x (A | B), 16 KB store staging, 16 KB residual staging, barriers, TMEM slot, bias
+  uint8_t* stg_base = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 32768);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;      // [2] accumulator complete
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (4 arrivals: one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* cb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) &
+                                       ~uintptr_t(15));   // [2 tile parities][2][256]
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = p.nkb_main + p.nkb_extra;
+  const uint32_t acc_cols = tmem_cols_for(p.BN);
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmA3);
+    }
+    if (p.nkb_extra > 0) tma_prefetch_desc(&tmAx);
+  }
+  if (warp == W_TMA && lane == 1) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 2u * acc_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == W_TMA) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint8_t* sa = smem;
+      const int cin = p.cin_blocks * BK;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % m_tiles, tn = tile / m_tiles;
+        const int bcol = tn * p.BN;
+        if (p.mode == EA_GEMM_LINEAR) {
+          const int arow = tm * BM;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, arow);
+            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+            sa += stage_bytes;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; sa = smem; }
+          }
+        } else {
+          int n0, h0, w0;
+          tile_origin(p, tm, n0, h0, w0);
+          int c0 = 0, kh = 0, kw = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            if (kb >= p.nkb_main) {
+              tma_load_4d(sa, &tmAx, &full_bar[stage], (kb - p.nkb_main) * BK, w0, h0, n0);
+            } else if (p.mode == EA_GEMM_CONV_S1) {
+              tma_load_4d(sa, &tmA0, &full_bar[stage], c0, w0 + kw - 1, h0 + kh - 1, n0);
+            } else {
+              const bool asym = p.mode == EA_GEMM_CONV_S2A;
+              const int ph = asym ? (kh == 1 ? 1 : 0) : (kh == 1 ? 0 : 1);
+              const int dh = asym ? (kh == 2 ? 1 : 0) : (kh == 0 ? -1 : 0);
+              const int pw = asym ? (kw == 1 ? 1 : 0) : (kw == 1 ? 0 : 1);
+              const int dw = asym ? (kw == 2 ? 1 : 0) : (kw == 0 ? -1 : 0);
+              const int sel = ph * 2 + pw;
+              const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
+              tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
+            }
+            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+            c0 += BK;
+            if (c0 == cin) { c0 = 0; if (++kw == 3) { kw = 0; ++kh; } }
+            sa += stage_bytes;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; sa = smem; }
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ============================ MMA issuer ==============================
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = umma_idesc(BM, (uint32_t)p.BN, 0, 0);
+    const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem), 1024);
+    const uint32_t st16 = (uint32_t)stage_bytes >> 4, ab16 = (uint32_t)a_bytes >> 4;
+    const int stages = p.stages;
+    uint64_t da = d0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int abuf = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[abuf], aphase ^ 1u);      // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t td = tb + (uint32_t)abuf * acc_cols;
+      uint32_t acc = 0u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t db = da + ab16;
+        if (elect_one()) {
+          umma_f16_ss(td, da, db, idesc, acc);
+          umma_f16_ss(td, da + 2, db + 2, idesc, 1u);
+          umma_f16_ss(td, da + 4, db + 4, idesc, 1u);
+          umma_f16_ss(td, da + 6, db + 6, idesc, 1u);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        acc = 1u;
+        da += st16;
+        if (++stage == stages) { stage = 0; phase ^= 1u; da = d0; }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[abuf]);
+      __syncwarp();
+      abuf ^= 1;
+      if (abuf == 0) aphase ^= 1u;
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int wq = warp;
+    const int r = wq * 32 + lane;
+    const int et = threadIdx.x;
+    const bool geglu = p.act == EA_ACT_GEGLU;
+    const int half_bn = p.BN >> 1;
+    const bool has_res = p.residual != nullptr;
+    uint4* stg = reinterpret_cast<uint4*>(stg_base + wq * 4096);
+    uint4* stg2 = reinterpret_cast<uint4*>(stg_base + 16384 + wq * 4096);
+    int abuf = 0, it = 0;
+    uint32_t fphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile % m_tiles, tn = tile / m_tiles;
+      const RowInfo ri = row_info(p, tm, r);
+      const int ncol0 = tn * p.BN;
+      float* cbt = cb + (it & 1) * 512;
+      const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
+      const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
+      uint4 rres[8];
+      if (!geglu) {
+        for (int i = et; i < p.BN; i += 128) {
+          const int col = ncol0 + i;
+          float v0 = 0.f, v1 = 0.f;
+          if (col < p.N) {
+            const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
+            v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
+            v1 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
+          }
+          cbt[i] = v0;
+          cbt[256 + i] = v1;
+        }
+        if (has_res) residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0, p.BN, p.N, lin_m0, p.M);
+      } else {
+        for (int i = et; i < p.BN; i += 128)
+          cbt[i] = (p.bias && ncol0 + i < p.N) ? __ldg(p.bias + ncol0 + i) : 0.f;
+      }
+      epi_bar_sync();
+      mbar_wait(&tfull_bar[abuf], fphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)abuf * acc_cols;
+      if (!geglu) {
+        const float* cbr = cbt + (ri.batch != b_first ? 256 : 0);
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, vb);
+        for (int c = 0; c < p.BN; c += 32) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = vb[j];
+          if (c + 32 < p.BN) tmem_ld32(taddr + (uint32_t)(c + 32), vb);
+          const int n_first = ncol0 + c;
+          const int half = (c >> 5) & 1;
+          if (has_res && half == 0) {
+            const int piece = lane & 7, rsub = lane >> 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rsub;
+              stg2[row * 8 + (piece ^ (row & 7))] = rres[i];
+            }
+            __syncwarp();
+            if (c + 64 < p.BN)
+              residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, n_first + 64, p.BN - c - 64, p.N, lin_m0, p.M);
+          }
+          {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
+              f[j] = __uint_as_float(va[j]) + b4.x;
+              f[j + 1] = __uint_as_float(va[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(va[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(va[j + 3]) + b4.w;
+            }
+            if (p.act == EA_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_SILU);
+            } else if (p.act == EA_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf_f(f[j]);
+            }
+            if (p.out_scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int slot = lane * 8 + ((half * 4 + q) ^ (lane & 7));
+              if (has_res) {
+                const uint4 rc = stg2[slot];
+                const float2 a = ea_unpack2(rc.x), b = ea_unpack2(rc.y), cc = ea_unpack2(rc.z), d = ea_unpack2(rc.w);
+                f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+                f[q * 8 + 4] += cc.x; f[q * 8 + 5] += cc.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+              }
+              stg[slot] = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                     ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
+            }
+          }
+          if (half == 1 || c + 32 >= p.BN)
+            stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
+                        half == 1 ? 8 : 4, p.N, lin_m0, p.M);
+        }
+      } else {
+        for (int c = 0; c < half_bn; c += 32) {
+          uint32_t xv[32], gv[32];
+          tmem_ld32(taddr + (uint32_t)c, xv);
+          tmem_ld32(taddr + (uint32_t)(half_bn + c), gv);
+          tmem_ld_wait();
+          float fx[32], fg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
+          uint4 o[4];
+          epilogue_geglu32(cbt, half_bn, c, fx, fg, o);
+          const int half = (c >> 5) & 1;
+          stage_put32(stg, lane, half, o);
+          if (half == 1 || c + 32 >= half_bn)
+            stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c - half * 32,
+                        half == 1 ? 8 : 4, p.N >> 1, lin_m0, p.M);
+        }
+      }
+      // every tcgen05.ld of this accumulator has completed (tmem_ld_wait above): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[abuf]);
+      abuf ^= 1;
+      if (abuf == 0) fphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2u * acc_cols);
+  }
+}
+
 // ---- launch planner -------------------------------------------------------------------
 // Picks (BN, stages, CTAs/SM, split-K) for one problem from a small cycle model: per K-block a CTA
 // needs max(MMA time, its share of chip bandwidth, TMA latency / stages in flight); small-M layers
@@ -1138,7 +1425,25 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
   static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
   const bool can_two = a->mode != EA_GEMM_CONV_S2 && a->mode != EA_GEMM_CONV_S2A && two_env != 0 && a->force_2cta >= 0;
-  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
+  // Persistent variant (experimental): wanted when forced, or with EA_GEMM_PERSIST=1 for multi-wave grids.
+  static const int persist_env = [] { const char* e = getenv("EA_GEMM_PERSIST"); return e ? atoi(e) : 0; }();
+  const bool batch_ok =
+      !a->rowvec || (a->mode == EA_GEMM_LINEAR
+                         ? (a->rows_per_batch == 0 || a->rows_per_batch >= BM || a->rows_per_batch == BM / 2)
+                         : p.bn <= 2);      // a tile may span at most two batch elements (fast epilogue)
+  const bool persist_ok = !a->out_f32 && !a->accumulate && a->force_splits <= 1 && a->force_2cta <= 0 &&
+                          (a->act == EA_ACT_GEGLU || batch_ok);
+  bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, persist ? 0 : ws_floats, sm_count(),
+                            can_two && !persist, a->residual != nullptr);
+  if (persist && a->force_persistent == 0) {
+    // auto mode: only grids of more than one wave gain from walking tiles inside a CTA
+    const long long tiles0 = (long long)m_tiles * ((a->N + plan.BN - 1) / plan.BN);
+    if (tiles0 <= sm_count()) {
+      persist = false;
+      plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
+    }
+  }
   if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
     plan.two = 1; plan.splits = 1; plan.kbps = nkb;
     if (plan.BN < 64) plan.BN = 64;
@@ -1180,6 +1485,32 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
                 (uint32_t)(two ? p.BN / 2 : p.BN)))
     return EA_ERR_TMAP;
 
+  if (persist && !two && p.splits == 1) {
+    const int sbp = BM * BK * 2 + p.BN * BK * 2;
+    const int fixed = 32768 + (2 * 8 + 4) * 8 + 32 + 2 * 2 * 256 * 4 + 1024;   // staging, barriers, slot, bias, align
+    int st = (224 * 1024 - fixed) / sbp;
+    if (st > 8) st = 8;
+    if (a->force_stages > 0 && a->force_stages < st) st = a->force_stages;
+    if (st >= 2) {
+      p.stages = st;
+      p.pair_release = 0;
+      const int smem_p = st * sbp + fixed;
+      static int max_set_p = 0;
+      if (smem_p > max_set_p) {
+        if (cudaFuncSetAttribute(ea_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_p) != cudaSuccess)
+          return EA_ERR_CUDA;
+        max_set_p = smem_p;
+      }
+      const int num_tiles = m_tiles * n_tiles;
+      const int grid_p = num_tiles < sm_count() ? num_tiles : sm_count();
+      cudaError_t lp = ea_launch(ea_gemm_persistent_kernel, dim3((unsigned)grid_p), dim3(GEMM_THREADS),
+                                 (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p, num_tiles,
+                                 m_tiles);
+      ea_count_launch();
+      return (lp == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
+    }
+  }
   const int stage_bytes = BM * BK * 2 + (two ? p.BN / 2 : p.BN) * BK * 2;
   int stages = plan.stages;
   if (stages > 8) stages = 8;

@@ -60,7 +60,8 @@ def gemm_workspace(device):
 def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
          conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
          out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
-         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0):
+         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0,
+         force_persistent=0):
     """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes."""
     lib = L.lib()
     g = L.GemmArgs()
@@ -110,6 +111,7 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     g.force_stages = force_stages
     g.force_splits = force_splits
     g.force_2cta = force_2cta
+    g.force_persistent = force_persistent
     g.no_spin = 1 if _CONCURRENT[0] else 0
     ws = gemm_workspace(a.device)
     g.workspace = ws.data_ptr()

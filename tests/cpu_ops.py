@@ -33,7 +33,7 @@ def _bump(n=1):
 def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, conv=None, a_extra=None,
          bias=None, rowvec=None, rows_per_batch=0, residual=None, out2=None, out_f32=None, act=0,
          out_scale=1.0, accumulate=False, ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0,
-         force_stages=0, force_splits=0, force_2cta=0):
+         force_stages=0, force_splits=0, force_2cta=0, force_persistent=0):
     _bump()
     Nn = w.shape[0]
     if mode == EA_GEMM_LINEAR:
