@@ -188,3 +188,45 @@ class _EncDec:
         self._dec, self.config = dec, dec.config
         self.decode_latents, self.decode, self.encode = dec.decode_latents, dec.decode, FakeVAE().encode
 
+
+def test_full_call_with_the_vae_engine_on_both_sides():
+    """`pipe.vae = VaeEngine`: the masked source image is encoded by the engine (prepare_masked_image_latents,
+    utils/...inpaint.py:1056-1105), the final blend uses those latents and the result is decoded by the engine
+    (decode_latents :718-724).  Re-enacted with the oracle VAE + oracle networks, same generator order."""
+    from editanything_b200.vae import VaeEngine, make_vae_state_dict
+    from editanything_b200.vae_spec import VaeConfig
+    from oracle import vae_oracle as V
+    vcfg = VaeConfig(ch=64, ch_mult=(1, 1, 1, 1), num_res_blocks=1)          # f = 8 like kl-f8, test-sized
+    vsd = dict(make_vae_state_dict(vcfg, 61, part="encoder"))
+    vsd.update(make_vae_state_dict(vcfg, 62))
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup(n_cn=1)
+    pipe = StableDiffusionControlNetInpaintPipeline(pipe.engine, vae=VaeEngine(vcfg, vsd, torch.device("cpu"), backend=cpu_ops))
+    assert pipe.vae_scale_factor == 8
+    steps, gs = 4, 7.0
+    out = pipe(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+               num_inference_steps=steps, guidance_scale=gs, generator=torch.manual_seed(11), prompt_embeds=pe,
+               negative_prompt_embeds=ne, output_type="np", controlnet_conditioning_scale=1.0,
+               num_images_per_prompt=1).images
+    # --- re-enactment -------------------------------------------------------------------------------
+    gen = torch.manual_seed(11)
+    lat = torch.randn((1, 4, 8, 8), generator=gen)                                       # prepare_latents
+    with torch.no_grad():                      # in_channels == 4 branch: the source image itself is encoded (:1469-1476)
+        mom = V.encode_moments(image, vsd, vcfg)
+    mean, logvar = mom.chunk(2, 1)
+    init = vcfg.scaling_factor * (mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * torch.randn(mean.shape, generator=gen))
+    m = 1 - F.interpolate((mask >= 0.5).float(), (8, 8), mode="nearest")
+    sch = DDIMScheduler()
+    sch.set_timesteps(steps)
+    ctx = torch.cat([ne, pe])
+    hints = [torch.cat([c] * 2) for c in conds]
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    for t in sch.timesteps:
+        with torch.no_grad():
+            e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], torch.cat([lat] * 2), torch.full((2,), int(t)), ctx, hints, [1.0])
+        lat = sch.step(e[:1] + gs * (e[1:] - e[:1]), t, lat).prev_sample
+    lat = init * m + lat * (1 - m)
+    with torch.no_grad():
+        ref = V.decode_latents(lat, vsd, vcfg).permute(0, 2, 3, 1).numpy()
+    assert out.shape == ref.shape == (1, 64, 64, 3)
+    assert abs(out - ref).max() < 2e-3
+
