@@ -879,7 +879,12 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // tile boundaries, and barrier setup / TMEM allocation / the dependency wait are paid once per SM instead
 // of once per tile.  Scope: no CTA pairs, no split-K, half output, epilogue = fast path or GEGLU (the host
 // only selects this kernel when every tile qualifies).
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EPI_WG = 2 (force_persistent = 2 / EA_GEMM_PERSIST=2): EIGHT epilogue warps, two per SM sub-partition - the
+// second warp-group takes every other 64-column group of the accumulator.  The one-warp-per-sub-partition
+// epilogue is instruction-latency bound (3-5 us per tile, profiles/r01p_exp_step_chain_gemm_in_context.txt);
+// a second warp on the same scheduler hides it, also for grids of a single wave.
+template <int EPI_WG>
+__global__ void __launch_bounds__(64 + 128 * EPI_WG, 1)
 ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                           const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmB,
@@ -890,12 +895,15 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
   const int a_bytes = BM * BK * 2;
   const int b_bytes = p.BN * BK * 2;
   const int stage_bytes = a_bytes + b_bytes;
-  // carve: [stages] x (A | B), 16 KB store staging, 16 KB residual staging, barriers, TMEM slot, bias
+  constexpr int EPI_WARPS = 4 * EPI_WG, EPI_THREADS = 128 * EPI_WG;
+  constexpr int PW_TMA = EPI_WARPS, PW_MMA = EPI_WARPS + 1;   // control warps keep the highest warp ids
+  // carve: [stages] x (A | B), 4 KB store staging + 4 KB residual staging per epilogue warp, barriers,
+  // TMEM slot, bias
   uint8_t* stg_base = smem + p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 32768);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + 2 * 4096 * EPI_WARPS);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;      // [2] accumulator complete
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (4 arrivals: one per epilogue warp)
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (one arrival per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* cb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) &
                                        ~uintptr_t(15));   // [2 tile parities][2][256]
@@ -906,7 +914,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
   const int nkb = p.nkb_main + p.nkb_extra;
   const uint32_t acc_cols = tmem_cols_for(p.BN);
 
-  if (warp == W_TMA && lane == 0) {
+  if (warp == PW_TMA && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
     if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
@@ -916,25 +924,25 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     }
     if (p.nkb_extra > 0) tma_prefetch_desc(&tmAx);
   }
-  if (warp == W_TMA && lane == 1) {
+  if (warp == PW_TMA && lane == 1) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], EPI_WARPS);
     }
     fence_mbar_init();
   }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, 2u * acc_cols);
+  if (warp == PW_MMA) tmem_alloc(tmem_slot, 2u * acc_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (warp == W_TMA) {
+  if (warp == PW_TMA) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
@@ -984,7 +992,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
         }
       }
     }
-  } else if (warp == W_MMA) {
+  } else if (warp == PW_MMA) {
     // ============================ MMA issuer ==============================
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = umma_idesc(BM, (uint32_t)p.BN, 0, 0);
@@ -1024,14 +1032,16 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     }
   } else {
     // ============================== epilogue ==============================
-    const int wq = warp;
+    const int wq = warp & 3;             // TMEM lane quarter = warp id mod 4
+    const int wg = warp >> 2;            // epilogue warp-group: owns the 64-column groups gi with gi % EPI_WG == wg
     const int r = wq * 32 + lane;
-    const int et = threadIdx.x;
+    const int et = threadIdx.x;          // 0 .. EPI_THREADS-1
     const bool geglu = p.act == EA_ACT_GEGLU;
     const int half_bn = p.BN >> 1;
     const bool has_res = p.residual != nullptr;
-    uint4* stg = reinterpret_cast<uint4*>(stg_base + wq * 4096);
-    uint4* stg2 = reinterpret_cast<uint4*>(stg_base + 16384 + wq * 4096);
+    uint4* stg = reinterpret_cast<uint4*>(stg_base + warp * 4096);
+    uint4* stg2 = reinterpret_cast<uint4*>(stg_base + 4096 * EPI_WARPS + warp * 4096);
+    constexpr int GSTEP = 64 * EPI_WG;   // column distance between two groups of one warp-group
     int abuf = 0, it = 0;
     uint32_t fphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -1043,7 +1053,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
       const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
       uint4 rres[8];
       if (!geglu) {
-        for (int i = et; i < p.BN; i += 128) {
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
           const int col = ncol0 + i;
           float v0 = 0.f, v1 = 0.f;
           if (col < p.N) {
@@ -1054,24 +1064,29 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           cbt[i] = v0;
           cbt[256 + i] = v1;
         }
-        if (has_res) residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0, p.BN, p.N, lin_m0, p.M);
+        if (has_res && wg * 64 < p.BN)
+          residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
       } else {
-        for (int i = et; i < p.BN; i += 128)
+        for (int i = et; i < p.BN; i += EPI_THREADS)
           cbt[i] = (p.bias && ncol0 + i < p.N) ? __ldg(p.bias + ncol0 + i) : 0.f;
       }
-      epi_bar_sync();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[abuf], fphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)abuf * acc_cols;
       if (!geglu) {
         const float* cbr = cbt + (ri.batch != b_first ? 256 : 0);
+        // this warp-group's chunks: both halves of the 64-column groups wg, wg + EPI_WG, ...; the next chunk's
+        // tcgen05.ld is in flight while the current one is converted and stored
         uint32_t va[32], vb[32];
-        tmem_ld32(taddr, vb);
-        for (int c = 0; c < p.BN; c += 32) {
+        int c = wg * 64;
+        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, vb);
+        while (c < p.BN) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) va[j] = vb[j];
-          if (c + 32 < p.BN) tmem_ld32(taddr + (uint32_t)(c + 32), vb);
+          const int nc = ((c & 32) == 0 && c + 32 < p.BN) ? c + 32 : (c & ~63) + GSTEP;
+          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
           const int n_first = ncol0 + c;
           const int half = (c >> 5) & 1;
           if (has_res && half == 0) {
@@ -1082,8 +1097,8 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
               stg2[row * 8 + (piece ^ (row & 7))] = rres[i];
             }
             __syncwarp();
-            if (c + 64 < p.BN)
-              residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, n_first + 64, p.BN - c - 64, p.N, lin_m0, p.M);
+            if (c + GSTEP < p.BN)
+              residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, n_first + GSTEP, p.BN - c - GSTEP, p.N, lin_m0, p.M);
           }
           {
             float f[32];
@@ -1122,8 +1137,9 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           if (half == 1 || c + 32 >= p.BN)
             stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
                         half == 1 ? 8 : 4, p.N, lin_m0, p.M);
+          c = nc;
         }
-      } else {
+      } else if (EPI_WG == 1) {
         for (int c = 0; c < half_bn; c += 32) {
           uint32_t xv[32], gv[32];
           tmem_ld32(taddr + (uint32_t)c, xv);
@@ -1140,6 +1156,21 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
             stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c - half * 32,
                         half == 1 ? 8 : 4, p.N >> 1, lin_m0, p.M);
         }
+      } else {
+        // two warp-groups: the 32-column output chunks alternate between them, each flushed on its own
+        for (int c = wg * 32; c < half_bn; c += 32 * EPI_WG) {
+          uint32_t xv[32], gv[32];
+          tmem_ld32(taddr + (uint32_t)c, xv);
+          tmem_ld32(taddr + (uint32_t)(half_bn + c), gv);
+          tmem_ld_wait();
+          float fx[32], fg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
+          uint4 o[4];
+          epilogue_geglu32(cbt, half_bn, c, fx, fg, o);
+          stage_put32(stg, lane, 0, o);
+          stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c, 4, p.N >> 1, lin_m0, p.M);
+        }
       }
       // every tcgen05.ld of this accumulator has completed (tmem_ld_wait above): hand it back
       tc_fence_before();
@@ -1152,7 +1183,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) {
+  if (warp == PW_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2u * acc_cols);
   }
@@ -1434,12 +1465,14 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   const bool persist_ok = !a->out_f32 && !a->accumulate && a->force_splits <= 1 && a->force_2cta <= 0 &&
                           (a->act == EA_ACT_GEGLU || batch_ok);
   bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
+  const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env == 2)) ? 2 : 1;
   GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, persist ? 0 : ws_floats, sm_count(),
                             can_two && !persist, a->residual != nullptr);
   if (persist && a->force_persistent == 0) {
-    // auto mode: only grids of more than one wave gain from walking tiles inside a CTA
+    // auto mode: only grids of more than one wave gain from walking tiles inside a CTA (the 8-epilogue-warp
+    // variant also takes single-wave grids: its gain is the faster epilogue)
     const long long tiles0 = (long long)m_tiles * ((a->N + plan.BN - 1) / plan.BN);
-    if (tiles0 <= sm_count()) {
+    if (persist_wg == 1 && tiles0 <= sm_count()) {
       persist = false;
       plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
     }
@@ -1487,7 +1520,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
 
   if (persist && !two && p.splits == 1) {
     const int sbp = BM * BK * 2 + p.BN * BK * 2;
-    const int fixed = 32768 + (2 * 8 + 4) * 8 + 32 + 2 * 2 * 256 * 4 + 1024;   // staging, barriers, slot, bias, align
+    const int fixed = 32768 * persist_wg + (2 * 8 + 4) * 8 + 32 + 2 * 2 * 256 * 4 + 1024;   // staging, barriers, slot, bias, align
     int st = (224 * 1024 - fixed) / sbp;
     if (st > 8) st = 8;
     if (a->force_stages > 0 && a->force_stages < st) st = a->force_stages;
@@ -1495,18 +1528,25 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       p.stages = st;
       p.pair_release = 0;
       const int smem_p = st * sbp + fixed;
-      static int max_set_p = 0;
-      if (smem_p > max_set_p) {
-        if (cudaFuncSetAttribute(ea_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 smem_p) != cudaSuccess)
-          return EA_ERR_CUDA;
-        max_set_p = smem_p;
+      static int max_set_p[3] = {0, 0, 0};
+      if (smem_p > max_set_p[persist_wg]) {
+        const cudaError_t se =
+            persist_wg == 2 ? cudaFuncSetAttribute(ea_gemm_persistent_kernel<2>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p)
+                            : cudaFuncSetAttribute(ea_gemm_persistent_kernel<1>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+        if (se != cudaSuccess) return EA_ERR_CUDA;
+        max_set_p[persist_wg] = smem_p;
       }
       const int num_tiles = m_tiles * n_tiles;
       const int grid_p = num_tiles < sm_count() ? num_tiles : sm_count();
-      cudaError_t lp = ea_launch(ea_gemm_persistent_kernel, dim3((unsigned)grid_p), dim3(GEMM_THREADS),
-                                 (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p, num_tiles,
-                                 m_tiles);
+      const cudaError_t lp =
+          persist_wg == 2 ? ea_launch(ea_gemm_persistent_kernel<2>, dim3((unsigned)grid_p), dim3(64 + 128 * 2),
+                                      (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p,
+                                      num_tiles, m_tiles)
+                          : ea_launch(ea_gemm_persistent_kernel<1>, dim3((unsigned)grid_p), dim3(64 + 128),
+                                      (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p,
+                                      num_tiles, m_tiles);
       ea_count_launch();
       return (lp == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
     }

@@ -108,9 +108,10 @@ typedef struct ea_gemm_args {
   int force_2cta;            /* 0 = auto; 1 = CTA pairs (tcgen05 cta_group::2, M = 256); -1 = never */
   int no_spin;               /* 1: split-K without the sibling wait - the last split CTA to arrive reduces
                                 the whole tile (required when other streams run kernels concurrently) */
-  int force_persistent;      /* 0 = auto (only with EA_GEMM_PERSIST=1 in the environment); 1 = persistent kernel
+  int force_persistent;      /* 0 = auto (only with EA_GEMM_PERSIST=1|2 in the environment); 1 = persistent kernel
                                 (one CTA per SM walks the tile list with two TMEM accumulators: EXPERIMENTAL,
-                                see DESIGN.md section 8) when the launch qualifies; -1 = never */
+                                see DESIGN.md section 8) when the launch qualifies; 2 = the same with eight
+                                epilogue warps (two per SM sub-partition); -1 = never */
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K

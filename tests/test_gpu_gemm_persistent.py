@@ -23,14 +23,17 @@ def _pair(fn):
     return a, b
 
 
+@pytest.mark.parametrize("variant", [1, 2])      # 1: four epilogue warps, 2: eight (two warp-groups)
 @pytest.mark.parametrize("M,N,K,res,act", [
     (8192, 2560, 320, False, "geglu"),      # 1280 tiles: ~9 per CTA
     (8192, 960, 320, False, "none"),        # qkv at 64x64
     (8192, 320, 1280, True, "none"),        # ff2 with residual
     (19000, 640, 192, True, "gelu"),        # ragged M, ragged last wave
     (300, 2048, 64, False, "none"),         # one K-block per tile
+    (8192, 320, 320, True, "none"),         # one wave, 96/160-wide tiles: odd number of 32-column chunks
+    (2048, 64, 640, False, "none"),         # tile narrower than one 64-column group: the 2nd warp-group idles
 ])
-def test_linear_matches_one_tile_kernel(M, N, K, res, act):
+def test_linear_matches_one_tile_kernel(M, N, K, res, act, variant):
     dev = torch.device("cuda:0")
     dt = ops.half_dtype()
     g = torch.Generator(device=dev).manual_seed(M + N + K)
@@ -43,13 +46,14 @@ def test_linear_matches_one_tile_kernel(M, N, K, res, act):
 
     def run(persist):
         out = torch.full((M, n_out), 7.0, device=dev, dtype=dt)
-        ops.gemm(x, w, out, bias=b, residual=r, act=code, force_persistent=1 if persist else -1, force_2cta=-1,
+        ops.gemm(x, w, out, bias=b, residual=r, act=code, force_persistent=variant if persist else -1, force_2cta=-1,
                  force_splits=1)
         return out
     ref, got = _pair(run)
     assert torch.equal(ref, got), float((ref.float() - got.float()).abs().max())
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,W,cin,cout,mode,extra", [
     (2, 64, 64, 320, 320, "s1", 0),
     (8, 96, 96, 320, 320, "s1", 0),        # SD2.1 768x768 N=4: 576 M-tiles
@@ -58,7 +62,7 @@ def test_linear_matches_one_tile_kernel(M, N, K, res, act):
     (2, 32, 32, 320, 320, "s2", 0),
     (1, 128, 128, 128, 128, "s2a", 0),
 ])
-def test_conv_matches_one_tile_kernel(B, H, W, cin, cout, mode, extra):
+def test_conv_matches_one_tile_kernel(B, H, W, cin, cout, mode, extra, variant):
     dev = torch.device("cuda:0")
     dt = ops.half_dtype()
     g = torch.Generator(device=dev).manual_seed(B * H + cin)
@@ -73,7 +77,7 @@ def test_conv_matches_one_tile_kernel(B, H, W, cin, cout, mode, extra):
     def run(persist):
         out = torch.full((B * H * W, cout), 7.0, device=dev, dtype=dt)
         ops.gemm(x, w, out, mode=m, conv=(B, H, W, cin), bias=b, rowvec=rv, a_extra=xe,
-                 ld_extra=extra, force_persistent=1 if persist else -1, force_2cta=-1, force_splits=1)
+                 ld_extra=extra, force_persistent=variant if persist else -1, force_2cta=-1, force_splits=1)
         return out
     ref, got = _pair(run)
     assert torch.equal(ref, got), float((ref.float() - got.float()).abs().max())

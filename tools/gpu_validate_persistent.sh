@@ -10,7 +10,9 @@ tail -8 gpurun_out/pytest_persistent.log
 if grep -q "failed\|error" gpurun_out/pytest_persistent.log; then echo "PERSISTENT KERNEL NOT VALID - stopping"; exit 0; fi
 timeout 500 python tools/gemm_breakdown.py gpurun_out/gemm_breakdown_base.json 2>&1 | head -12
 EA_GEMM_PERSIST=1 timeout 500 python tools/gemm_breakdown.py gpurun_out/gemm_breakdown_persist.json 2>&1 | head -12
+EA_GEMM_PERSIST=2 timeout 500 python tools/gemm_breakdown.py gpurun_out/gemm_breakdown_persist2.json 2>&1 | head -12
 ( time EA_GEMM_PERSIST=1 timeout 900 python -m pytest tests -m gpu -q -x ) > gpurun_out/pytest_gpu_persist.log 2>&1
 tail -4 gpurun_out/pytest_gpu_persist.log
 EA_GEMM_PERSIST=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c1-700
+EA_GEMM_PERSIST=2 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c1-700
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c1-400
