@@ -1466,17 +1466,17 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
                           (a->act == EA_ACT_GEGLU || batch_ok);
   bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
   const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env == 2)) ? 2 : 1;
-  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, persist ? 0 : ws_floats, sm_count(),
-                            can_two && !persist, a->residual != nullptr);
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
   if (persist && a->force_persistent == 0) {
-    // auto mode: only grids of more than one wave gain from walking tiles inside a CTA (the 8-epilogue-warp
-    // variant also takes single-wave grids: its gain is the faster epilogue)
+    // auto mode (environment switch): never where the planner splits K (weight-streaming small-M layers; first
+    // A/B on hardware: the unsplit 8x8 convolutions took 50 us instead of 20), and the 4-epilogue-warp variant only
+    // for grids of more than one wave (its gain is the overlap across tiles; the 8-warp variant also speeds up
+    // the epilogue of a single tile)
     const long long tiles0 = (long long)m_tiles * ((a->N + plan.BN - 1) / plan.BN);
-    if (persist_wg == 1 && tiles0 <= sm_count()) {
-      persist = false;
-      plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
-    }
+    if (plan.splits > 1 || (persist_wg == 1 && tiles0 <= sm_count())) persist = false;
   }
+  if (persist && (plan.two || plan.splits > 1))   // the persistent kernel has no CTA pairs and no split-K
+    plan = plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, a->residual != nullptr);
   if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
     plan.two = 1; plan.splits = 1; plan.kbps = nkb;
     if (plan.BN < 64) plan.BN = 64;
