@@ -1203,10 +1203,14 @@ struct GemmPlan { int BN, stages, splits, kbps, occ; double cost; int two; };
 // column in the epilogue (+21 with a residual) because ONE warp per SM sub-partition drains TMEM,
 // converts and stores with nothing to hide its instruction latencies.
 static constexpr double PL_LAT = 2100.0, PL_SM_CAP = 57.0, PL_L2 = 8000.0, PL_HBM = 3400.0;
-#ifndef PL_SPLIT_COL
-#define PL_SPLIT_COL 8.0
-#define PL_SPLIT_FIX 7000.0
-#endif
+// Experiment hook: the two split-K constants can be overridden from the environment (EA_PL_SPLIT_COL,
+// EA_PL_SPLIT_FIX) so several settings can be A/B-ed in one GPU session without rebuilding.
+static double pl_env(const char* name, double dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atof(e) : dflt;
+}
+static const double PL_SPLIT_COL = pl_env("EA_PL_SPLIT_COL", 8.0);
+static const double PL_SPLIT_FIX = pl_env("EA_PL_SPLIT_FIX", 7000.0);
 static constexpr double PL_START = 3800.0, PL_START_TWO = 2100.0, PL_EPI = 50.0, PL_EPI_RES = 21.0;
 
 static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm,

@@ -95,6 +95,8 @@ def main():
                      "tflops": round(fl / us / 1e6, 1), "total_ms": round(us * len(recs) / 1e3, 3), "kb": kb,
                      "plan": list(out5)})
     rows.sort(key=lambda r: -r["total_ms"])
+    if len(sys.argv) > 1:       # first: a closed stdout pipe (| head) must not lose the data
+        json.dump(rows, open(sys.argv[1], "w"), indent=0)
     tot = sum(r["total_ms"] for r in rows)
     print(f"{len(probe.records)} gemm launches, {len(rows)} signatures, sum of isolated times {tot:.3f} ms")
     print("mode      M     N      K act res acc  n      us  TFLOP/s  total_ms  cum%  kb plan[bn,stages,splits,occ,two]")
@@ -104,8 +106,6 @@ def main():
         print(f"{r['mode']:3d} {r['M']:6d} {r['N']:5d} {r['K']:6d} {r['act']:3d} {int(r['res']):3d} {int(r['acc']):3d} {r['n']:3d} "
               f"{r['us']:7.2f} {r['tflops']:8.1f} {r['total_ms']:9.3f} {100 * cum / tot:5.1f} {r['kb']:4d} {r['plan']}"
               f"{' x' if r['extra'] else ''}{' rv' if r['rowvec'] else ''}{' o2' if r['out2'] else ''}{' f32' if r['f32'] else ''}")
-    if len(sys.argv) > 1:
-        json.dump(rows, open(sys.argv[1], "w"), indent=0)
 
 
 if __name__ == "__main__":
