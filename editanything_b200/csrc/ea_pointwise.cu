@@ -350,10 +350,14 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
                                     const float* __restrict__ bias, float* __restrict__ latents,
                                     float* __restrict__ eps_out, const float* __restrict__ coef,
                                     float guidance, const float* __restrict__ known,
+                                    const float* __restrict__ noise,
                                     const float* __restrict__ mask, ea_half* __restrict__ lat_half,
-                                    int Nimg, int H, int W, int C) {
+                                    int* __restrict__ step_ctr, int Nimg, int H, int W, int C) {
   pdl_launch_dependents();
   pdl_wait();
+  // device-side step counter of the captured loop: the first kernel of the step (step_gather_kernel) read it,
+  // this last one advances it - stream order makes that race-free
+  if (step_ctr && blockIdx.x == 0 && threadIdx.x == 0) *step_ctr = *step_ctr + 1;
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long npix = (long long)Nimg * H * W;
@@ -415,8 +419,16 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
       float x0 = (xt - s1a * e) / sa;       // :215
       float xp = sap * x0 + s1ap * e;       // :226-230 (eta = 0)
       if (known) {
+        // inpaint blend (utils/stable_diffusion_controlnet_inpaint.py:1647-1656).  With `noise` the kept
+        // region is re-noised here: add_noise(init, noise, t_next) = coef[4] * init + coef[5] * noise, and
+        // coef[6] switches the blend per step (alignment_ratio window) without touching the launch.
         float mk = mask[gw];
-        xp = known[gw * 4 + o] * mk + xp * (1.f - mk);
+        float kn = known[gw * 4 + o];
+        if (noise) {
+          kn = coef[4] * kn + coef[5] * noise[gw * 4 + o];
+          mk *= coef[6];
+        }
+        xp = kn * mk + xp * (1.f - mk);
       }
       latents[gw * 4 + o] = xp;
       if (lat_half) {
@@ -424,6 +436,29 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
         lat_half[(gw + npix) * 4 + o] = ea_f2h(xp);
       }
     }
+  }
+}
+
+// ---------------- per-step table gather (first kernel of a captured denoising step) -------------
+// Everything that changes from step to step (the scheduler coefficients and every net's time-embedding rows)
+// lives in device tables with one row per step; this kernel copies row min(*ctr, n_rows - 1) of each table into
+// the fixed buffers the captured step reads, so the host's per-step work is ONE graph launch.
+struct StepTables {
+  int n;
+  const float* src[EA_STEP_MAX_TABLES];
+  float* dst[EA_STEP_MAX_TABLES];
+  long long row_elems[EA_STEP_MAX_TABLES];
+};
+__global__ void step_gather_kernel(const int* __restrict__ ctr, int n_rows, const StepTables tb) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int row = *ctr;
+  row = row < 0 ? 0 : (row >= n_rows ? n_rows - 1 : row);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < tb.n; ++k) {
+    const float* s = tb.src[k] + (long long)row * tb.row_elems[k];
+    float* d = tb.dst[k];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tb.row_elems[k]; i += stride) d[i] = __ldg(s + i);
   }
 }
 
@@ -808,16 +843,33 @@ extern "C" int ea_timestep_embedding(const float* t, float* out, int B, int dim,
 
 extern "C" int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
                                float* eps_out, const float* coef, float guidance,
-                               const float* known, const float* mask, void* lat_half_out, int Nimg,
-                               int H, int W, int C, void* stream) {
+                               const float* known, const float* noise, const float* mask, void* lat_half_out,
+                               int* step_counter, int Nimg, int H, int W, int C, void* stream) {
   if (!xn || !w || !bias || (!latents && !eps_out)) return EA_ERR_ARG;
   if (latents && !coef) return EA_ERR_ARG;
-  if (known && !mask) return EA_ERR_ARG;
+  if ((known && !mask) || (noise && !known)) return EA_ERR_ARG;
   if (C % 8 != 0) return EA_ERR_SHAPE;
   long long npix = (long long)Nimg * H * W;
   const int wpc = 4;
-  ea_launch(out_cfg_ddim_kernel, dim3((unsigned)((npix + wpc - 1) / wpc)), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, mask,
-      reinterpret_cast<ea_half*>(lat_half_out), Nimg, H, W, C);
+  ea_launch(out_cfg_ddim_kernel, dim3((unsigned)((npix + wpc - 1) / wpc)), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, noise, mask,
+      reinterpret_cast<ea_half*>(lat_half_out), step_counter, Nimg, H, W, C);
+  return EA_LAUNCH_OK();
+}
+
+extern "C" int ea_step_gather(const int* step_counter, int n_rows, int n_tables, const float* const* src,
+                              float* const* dst, const long long* row_elems, void* stream) {
+  if (!step_counter || n_rows <= 0 || n_tables <= 0 || n_tables > EA_STEP_MAX_TABLES || !src || !dst || !row_elems)
+    return EA_ERR_ARG;
+  StepTables tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.n = n_tables;
+  long long total = 0;
+  for (int k = 0; k < n_tables; ++k) {
+    if (!src[k] || !dst[k] || row_elems[k] <= 0) return EA_ERR_ARG;
+    tb.src[k] = src[k]; tb.dst[k] = dst[k]; tb.row_elems[k] = row_elems[k];
+    total += row_elems[k];
+  }
+  ea_launch(step_gather_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, EA_STREAM(stream), step_counter, n_rows, tb);
   return EA_LAUNCH_OK();
 }
 

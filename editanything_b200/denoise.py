@@ -88,14 +88,16 @@ class DenoiseEngine:
             nets = [self.unet] + self.cns
             self.emb_bufs = [torch.zeros(self.B, n.emb_total, device=self.dev, dtype=torch.float32) for n in nets]
             self.t_dev = torch.zeros(self.B, device=self.dev, dtype=torch.float32)
-            self.coef_dev = torch.zeros(4, device=self.dev, dtype=torch.float32)
+            self.coef_dev = torch.zeros(8, device=self.dev, dtype=torch.float32)
+            self.step_ctr = torch.zeros(1, device=self.dev, dtype=torch.int32)
             self.gn_ws = torch.zeros(self.B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
+            self._sched_key, self._sched_cap, self.n_steps = None, 0, 0
             self._graph = None
 
-    def _fill_emb(self, t):
-        """Time-embedding rows for timestep t into the fixed buffers the (captured) step reads.
-        Computed once per distinct t (util.py:154-174 + time_embed + every ResBlock emb_layers,
-        openaimodel.py:526-531,204-210) and cached: the DDIM table repeats for every image."""
+    def _emb_rows(self, t):
+        """Time-embedding rows of every net for timestep t (util.py:154-174 + time_embed + every ResBlock
+        emb_layers, openaimodel.py:526-531,204-210): computed once per distinct t and cached - the DDIM table
+        repeats for every image."""
         key = float(t)
         rows = self._emb_cache.get(key)
         if rows is None:
@@ -103,13 +105,47 @@ class DenoiseEngine:
             rows = [e.clone() for e in self.runner.compute_embs(self.t_dev, self.B)]
             if len(self._emb_cache) < 1100:
                 self._emb_cache[key] = rows
-        for buf, r in zip(self.emb_bufs, rows):
+        return rows
+
+    def _fill_emb(self, t):
+        for buf, r in zip(self.emb_bufs, self._emb_rows(t)):
             buf.copy_(r)
+
+    # -- the sampling schedule as device tables -------------------------------------------------
+    def set_schedule(self, timesteps, alphas, alphas_prev, blend=None):
+        """Everything that changes from step to step of the loop (utils/...inpaint.py:1540-1656), as device
+        tables with one row per step: the DDIM coefficients (cldm/ddim_hacked.py:203-231), the per-ResBlock
+        time-embedding rows of every net, and the inpaint-blend terms.  `blend` = (k_init[S], k_noise[S],
+        on[S]): the kept region of step i is k_init[i] * known + k_noise[i] * noise (add_noise at
+        timesteps[i + 1], :1650-1652), applied where on[i] (i < len * alignment_ratio, :1648).  Without `blend`
+        the kept region is `known` itself on every step.  The captured step indexes the tables with a device
+        counter (ea_step_gather), so the host issues ONE graph launch per step."""
+        ts = [float(t) for t in timesteps]
+        S = len(ts)
+        if blend is None:
+            blend = ([1.0] * S, [0.0] * S, [1.0] * S)
+        rows = [[math.sqrt(a), math.sqrt(1.0 - a), math.sqrt(ap), math.sqrt(1.0 - ap), float(ki), float(kn), float(on), 0.0]
+                for a, ap, ki, kn, on in zip(alphas, alphas_prev, *blend)]
+        key = (tuple(ts), tuple(map(tuple, rows)), self.B)
+        if key == self._sched_key:
+            return
+        if S > self._sched_cap:
+            cap = ((S + 63) // 64) * 64
+            self.coef_tab = torch.zeros(cap, 8, device=self.dev, dtype=torch.float32)
+            self.emb_tabs = [torch.zeros(cap, *b.shape, device=self.dev, dtype=torch.float32) for b in self.emb_bufs]
+            self._sched_cap = cap
+            self._graph = None        # table addresses are baked into the captured step
+        self.coef_tab[:S].copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=True)
+        for i, t in enumerate(ts):
+            for tab, r in zip(self.emb_tabs, self._emb_rows(t)):
+                tab[i].copy_(r)
+        self.n_steps = S
+        self._sched_key = key
 
     # -- parity API: the network output itself ------------------------------------------------
     def eps(self, x_nchw, t):
         """eps = unet(x, t, ctx, control=sum_k scale_k * controlnet_k(x, hint_k, t, ctx)) as fp32
-        NCHW — the quantity the reference calls `noise_pred` before guidance."""
+        NCHW - the quantity the reference calls `noise_pred` before guidance."""
         B, C, H, W_ = x_nchw.shape
         xh = x_nchw.to(self.dev).permute(0, 2, 3, 1).contiguous().to(self.hdt)
         self._fill_emb(t)
@@ -123,42 +159,65 @@ class DenoiseEngine:
     # -- production API: one fused denoising step ----------------------------------------------
     def _step_body(self):
         H, W_ = self.lat.shape[1], self.lat.shape[2]
+        self.ops.step_gather(self.step_ctr, self._sched_cap, [self.coef_tab] + self.emb_tabs,
+                             [self.coef_dev] + self.emb_bufs)
         xn = self.runner.eps_features(self.x_half, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws,
                                       embs=self.emb_bufs)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], latents=self.lat,
-                              coef=self.coef_dev, guidance=self.guidance, known=self.known, mask=self.mask,
-                              lat_half_out=self.x_half, Nimg=self.B // 2, H=H, W=W_, C_=self.cfg.model_channels)
+                              coef=self.coef_dev, guidance=self.guidance, known=self.known, noise=self.noise,
+                              mask=self.mask, lat_half_out=self.x_half, step_counter=self.step_ctr,
+                              Nimg=self.B // 2, H=H, W=W_, C_=self.cfg.model_channels)
 
-    def begin(self, latents_nchw, guidance, known_nchw=None, mask_n1hw=None, use_graph=True):
-        """latents: fp32 [N, 4, h, w] initial noise (N = B/2 images).  known/mask: optional inpaint
-        blend tensors (mask == 1 keeps `known`, utils/...inpaint.py:1484-1489,1647-1664)."""
-        lat = latents_nchw.to(self.dev, torch.float32).permute(0, 2, 3, 1).contiguous()
+    def begin(self, latents_nchw, guidance, known_nchw=None, mask_n1hw=None, noise_nchw=None, use_graph=True):
+        """latents: fp32 [N, 4, h, w] initial noise (N = B/2 images).  known/mask: optional inpaint blend
+        tensors (mask == 1 keeps `known`, utils/...inpaint.py:1484-1489,1647-1664); noise: the initial latent
+        noise the kept region is re-noised with (:1446,1650).  The blend buffers always exist (an all-zero mask
+        is an exact no-op), so switching the blend on, off or ending its window never re-captures the graph."""
+        def nhwc(t):
+            return t.to(self.dev, torch.float32).permute(0, 2, 3, 1).contiguous()
+        lat = nhwc(latents_nchw)
         self._keep("lat", lat)
         self._keep("x_half", torch.cat([lat, lat]).to(self.hdt).contiguous())
         if getattr(self, "guidance", None) != float(guidance):
             self._graph = None
         self.guidance = float(guidance)
-        if known_nchw is None:
-            if getattr(self, "known", None) is not None:
-                self._graph = None
-            self.known = self.mask = None
+        zeros = torch.zeros_like(lat)
+        self._keep("known", nhwc(known_nchw) if known_nchw is not None else zeros)
+        self._keep("noise", nhwc(noise_nchw) if noise_nchw is not None else zeros)
+        if known_nchw is not None:
+            m = mask_n1hw.to(self.dev, torch.float32).reshape(lat.shape[0], lat.shape[1], lat.shape[2]).contiguous()
         else:
-            self._keep("known", known_nchw.to(self.dev, torch.float32).permute(0, 2, 3, 1).contiguous())
-            self._keep("mask", mask_n1hw.to(self.dev, torch.float32).reshape(lat.shape[0], lat.shape[1],
-                                                                            lat.shape[2]).contiguous())
+            m = zeros[..., 0].contiguous()
+        self._keep("mask", m)
         use = use_graph and self.ops is _cuda_ops
         if use != getattr(self, "_use_graph", None):
             self._graph = None
         self._use_graph = use
+        self.step_ctr.zero_()
+
+    def end_blend(self):
+        """Close the blend window from the host (callers that drive the blend themselves)."""
+        self.mask.zero_()
+
+    def blend_now(self, k_init, k_noise):
+        """latents = (k_init * known + k_noise * noise) * mask + latents * (1 - mask), outside the fused step
+        (utils/...inpaint.py:1647-1656) - for callers that must observe the un-blended latents first."""
+        m = self.mask[..., None]
+        self.lat.copy_((k_init * self.known + k_noise * self.noise) * m + self.lat * (1 - m))
+        self.x_half.copy_(torch.cat([self.lat, self.lat]).to(self.hdt))
 
     def set_known(self, known_nchw):
         self.known.copy_(known_nchw.to(self.dev, torch.float32).permute(0, 2, 3, 1))
 
-    def step(self, t, a_t, a_prev):
-        """One DDIM (eta=0) step at timestep t (cldm/ddim_hacked.py:181-231)."""
-        self._fill_emb(t)
-        self.coef_dev.copy_(torch.tensor([math.sqrt(a_t), math.sqrt(1.0 - a_t), math.sqrt(a_prev),
-                                          math.sqrt(1.0 - a_prev)], dtype=torch.float32), non_blocking=True)
+    def step(self, t=None, a_t=None, a_prev=None):
+        """One fused step.  Without arguments: step number *step_ctr of the schedule given to set_schedule()
+        (host work: one graph launch).  With (t, a_t, a_prev): a single DDIM (eta=0) step at timestep t
+        (cldm/ddim_hacked.py:181-231) - a one-row schedule."""
+        if t is not None:
+            self.set_schedule([t], [a_t], [a_prev])
+            self.step_ctr.zero_()
+        elif self._sched_key is None:
+            raise RuntimeError("set_schedule() first, or pass (t, a_t, a_prev)")
         if not self._use_graph:
             self._step_body()
             return
@@ -166,12 +225,13 @@ class DenoiseEngine:
             # warm-up on a side stream (allocator + cudaFuncSetAttribute), then capture once
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
-            lat0, xh0 = self.lat.clone(), self.x_half.clone()
+            lat0, xh0, c0 = self.lat.clone(), self.x_half.clone(), self.step_ctr.clone()
             with torch.cuda.stream(s):
                 self._step_body()
             torch.cuda.current_stream().wait_stream(s)
             self.lat.copy_(lat0)
             self.x_half.copy_(xh0)
+            self.step_ctr.copy_(c0)
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launch_count()
             with torch.cuda.graph(g):
@@ -180,6 +240,7 @@ class DenoiseEngine:
             self._graph = g
             self.lat.copy_(lat0)
             self.x_half.copy_(xh0)
+            self.step_ctr.copy_(c0)
         self._graph.replay()
 
     def latents(self):

@@ -203,12 +203,22 @@ def timestep_embedding(t, out, *, B, dim):
     return out
 
 
-def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None,
-                 mask=None, lat_half_out=None, Nimg, H, W, C_):
+def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, noise=None,
+                 mask=None, lat_half_out=None, step_counter=None, Nimg, H, W, C_):
     lib = L.lib()
     L.check(lib.ea_out_cfg_ddim(_p(xn), _p(w), _p(bias), _p(latents), _p(eps_out), _p(coef),
-                                float(guidance), _p(known), _p(mask), _p(lat_half_out), Nimg, H, W,
-                                C_, _stream()), "ea_out_cfg_ddim")
+                                float(guidance), _p(known), _p(noise), _p(mask), _p(lat_half_out),
+                                _p(step_counter), Nimg, H, W, C_, _stream()), "ea_out_cfg_ddim")
+
+
+def step_gather(step_counter, n_rows, tables, dsts):
+    """dsts[k][:] = tables[k][min(*step_counter, n_rows - 1)] for fp32 tables [rows, ...] (one launch)."""
+    lib = L.lib()
+    n = len(tables)
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in tables])
+    dst = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
+    rows = (C.c_longlong * n)(*[d.numel() for d in dsts])
+    L.check(lib.ea_step_gather(_p(step_counter), int(n_rows), n, src, dst, rows, _stream()), "ea_step_gather")
 
 
 def sam_relpos(q, q_bs, q_ns, Rh, Rw, rel_h, rel_w, *, B, heads, S, d):

@@ -306,6 +306,9 @@ class StableDiffusionControlNetInpaintPipeline:
         if self.vae is None:
             raise ValueError("a VAE is required to encode `image`")
         masked_image = masked_image.to(dtype=dtype)
+        vdev = self._vae_device()
+        if vdev is not None:
+            masked_image = masked_image.to(vdev)          # the reference's `.to(device=device, dtype=dtype)` (:1068)
         if isinstance(generator, list):
             lat = torch.cat([self.vae.encode(masked_image[i:i + 1]).latent_dist.sample(generator=generator[i])
                              for i in range(batch_size)], dim=0)
@@ -317,6 +320,29 @@ class StableDiffusionControlNetInpaintPipeline:
                 raise ValueError("The passed images and the required batch size don't match.")
             lat = lat.repeat(batch_size // lat.shape[0], 1, 1, 1)
         return lat
+
+    def _vae_device(self):
+        v = self.vae
+        for attr in ("device", "dev"):
+            d = getattr(v, attr, None)
+            if isinstance(d, (torch.device, str)):
+                return torch.device(d)
+        if hasattr(v, "parameters"):
+            try:
+                return next(iter(v.parameters())).device
+            except StopIteration:
+                return None
+        return None
+
+    def run_safety_checker(self, image, device, dtype):
+        """utils/...inpaint.py:705-716."""
+        if self.safety_checker is not None:
+            safety_checker_input = self.feature_extractor(self.numpy_to_pil(image), return_tensors="pt").to(device)
+            image, has_nsfw_concept = self.safety_checker(images=image,
+                                                          clip_input=safety_checker_input.pixel_values.to(dtype))
+        else:
+            has_nsfw_concept = None
+        return image, has_nsfw_concept
 
     def decode_latents(self, latents):
         """utils/...inpaint.py:718-724.  A `VaeDecoderEngine` (editanything_b200.vae) does the 1/scaling_factor,
@@ -390,6 +416,7 @@ class StableDiffusionControlNetInpaintPipeline:
             m = m.repeat(N // m.shape[0], 1, 1, 1)
 
         eng = self.engine
+        dev = eng.dev
         eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale)
         fused = isinstance(self.scheduler, DDIMScheduler)
         n_t = len(timesteps)
@@ -397,23 +424,32 @@ class StableDiffusionControlNetInpaintPipeline:
         if blend_steps and blend_steps >= n_t:
             # the reference indexes timesteps[i + 1] (:1652): alignment_ratio = 1.0 raises there too
             raise IndexError("alignment_ratio covers the last step: timesteps[i + 1] is out of range")
+        # everything below lives on the execution device (the noise was DRAWN on the generator's device above,
+        # like diffusers' randn_tensor, then moved - utils/...inpaint.py:998-1012)
+        lat = lat.to(dev, torch.float32)
+        noise_d, init_d, m_d = noise.to(dev, torch.float32), init_lat.to(dev, torch.float32), m.to(dev, torch.float32)
         if fused:
-            eng.begin(lat.float(), guidance_scale, known_nchw=init_lat.float() if blend_steps else None,
-                      mask_n1hw=m.float() if blend_steps else None)
+            acp = self.scheduler.alphas_cumprod
+            coefs = [self.scheduler.coefficients(t) for t in timesteps]
+            # the kept region of step i is add_noise(init, noise, timesteps[i + 1]) while i < len * alignment_ratio
+            # (:1647-1656).  With a callback the blend runs on the host side AFTER the callback, like the reference
+            # (:1640-1656 calls back with the un-blended latents); otherwise it is fused into the step's last kernel.
+            host_blend = callback is not None and blend_steps > 0
+            k_next = [(math.sqrt(float(acp[int(timesteps[i + 1])])), math.sqrt(1.0 - float(acp[int(timesteps[i + 1])])))
+                      if i < blend_steps else (1.0, 0.0) for i in range(n_t)]
+            on = [1.0 if (i < blend_steps and not host_blend) else 0.0 for i in range(n_t)]
+            eng.set_schedule([int(t) for t in timesteps], [c[0] for c in coefs], [c[1] for c in coefs],
+                             blend=([k[0] for k in k_next], [k[1] for k in k_next], on))
+            eng.begin(lat, guidance_scale, known_nchw=init_d if blend_steps else None,
+                      mask_n1hw=m_d if blend_steps else None, noise_nchw=noise_d if blend_steps else None)
             for i, t in enumerate(timesteps):
-                blending = i < blend_steps
-                if blending:
-                    eng.set_known(self.scheduler.add_noise(init_lat.float(), noise.float(), timesteps[i + 1]))
-                elif blend_steps and i == blend_steps:
-                    eng.begin(eng.latents(), guidance_scale)           # blend window over: plain steps
-                a_t, a_prev = self.scheduler.coefficients(t)
-                eng.step(int(t), a_t, a_prev)
+                eng.step()
                 if callback is not None and i % callback_steps == 0:
                     callback(i, t, eng.latents())
+                if host_blend and i < blend_steps:
+                    eng.blend_now(k_next[i][0], k_next[i][1])
             lat = eng.latents()
         else:
-            lat = lat.to(eng.dev, torch.float32)
-            init_d, noise_d, m_d = init_lat.to(eng.dev).float(), noise.to(eng.dev).float(), m.to(eng.dev).float()
             for i, t in enumerate(timesteps):
                 x_in = self.scheduler.scale_model_input(torch.cat([lat] * 2), t)
                 eps = eng.eps(x_in, float(t))
@@ -424,8 +460,7 @@ class StableDiffusionControlNetInpaintPipeline:
                 if i < blend_steps:
                     lat = self.scheduler.add_noise(init_d, noise_d, timesteps[i + 1]) * m_d + lat * (1 - m_d)
         if alignment_ratio is None or alignment_ratio == 1.0:
-            dev = lat.device
-            lat = init_lat.to(dev).float() * m.to(dev).float() + lat * (1 - m.to(dev).float())   # :1658-1664
+            lat = init_d * m_d + lat * (1 - m_d)                                   # :1658-1664
 
         if output_type == "latent":
             images, nsfw = lat, None
@@ -434,7 +469,7 @@ class StableDiffusionControlNetInpaintPipeline:
                 raise ValueError("a VAE is required unless output_type='latent'")
             images = self.decode_latents(lat.to(next(iter(self.vae.parameters())).dtype)
                                          if hasattr(self.vae, "parameters") else lat)
-            nsfw = None
+            images, nsfw = self.run_safety_checker(images, dev, edt)
             if output_type == "pil":
                 images = self.numpy_to_pil(images)
         if not return_dict:

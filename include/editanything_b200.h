@@ -199,14 +199,28 @@ int ea_timestep_embedding(const float* t, float* out, int B, int dim, void* stre
  * xn: NHWC half [2*Nimg, H, W, C] (first Nimg = unconditional, last Nimg = conditional);
  * w: fp32 [4, 3, 3, C]; bias fp32 [4]; latents fp32 NHWC [Nimg, H, W, 4] updated in place;
  * eps_out (optional) fp32 [2*Nimg, H, W, 4] raw network output;
- * coef: device fp32 [4] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)};
- * blend (optional): known fp32 NHWC [Nimg,H,W,4], mask fp32 [Nimg,H,W] (1 = keep known).
+ * coef: device fp32 [8] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev), k_init, k_noise, blend_on, 0};
+ * blend (optional): known fp32 NHWC [Nimg,H,W,4], mask fp32 [Nimg,H,W] (1 = keep known).  With `noise`
+ *   (optional, fp32 like known) the kept region is add_noise(known, noise, t_next) = k_init * known +
+ *   k_noise * noise (utils/stable_diffusion_controlnet_inpaint.py:1650-1656) and blend_on (0 / 1) gates the
+ *   blend per step (the alignment_ratio window, :1648) - all per-step state is in `coef`.
  * lat_half_out (optional): half NHWC [2*Nimg,H,W,4] = updated latents duplicated for next step.
+ * step_counter (optional): device int incremented by one (the captured-loop step index, see ea_step_gather).
  */
 int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
                     float* eps_out, const float* coef, float guidance, const float* known,
-                    const float* mask, void* lat_half_out, int Nimg, int H, int W, int C,
-                    void* stream);
+                    const float* noise, const float* mask, void* lat_half_out, int* step_counter,
+                    int Nimg, int H, int W, int C, void* stream);
+
+/* ---- ea_step_gather: first kernel of a captured denoising step ---------------------------------
+ * The loop of utils/stable_diffusion_controlnet_inpaint.py:1540-1656 changes only scalars from step to step
+ * (scheduler coefficients, the timestep behind every ResBlock's emb_layers projection, openaimodel.py:204-210).
+ * They live in device tables with one row per step; this launch copies row min(*step_counter, n_rows-1) of
+ * each of the n_tables (<= EA_STEP_MAX_TABLES) fp32 tables src[k] (row_elems[k] floats per row) into dst[k],
+ * the fixed buffers the rest of the step reads.  Host work per step: one CUDA-graph launch. */
+#define EA_STEP_MAX_TABLES 8
+int ea_step_gather(const int* step_counter, int n_rows, int n_tables, const float* const* src,
+                   float* const* dst, const long long* row_elems, void* stream);
 
 /* ---- SAM helpers ---------------------------------------------------------------------------
  * ea_sam_relpos: rel_h[bh, q, kh] = sum_c q[bh, q, c] * Rh[qh(q), kh, c] (and rel_w), the

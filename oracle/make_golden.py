@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import torch
 
-from editanything_b200.unet_spec import SD15, TINY, TINY21, make_state_dict
+from editanything_b200.unet_spec import SD15, SD21, TINY, TINY21, make_state_dict
 from oracle import ref_shim
 from oracle.inputs import make_inputs
 
@@ -27,9 +27,20 @@ CASES = {
     "tiny_sd15_32": (TINY, 2, 32, 77, [741], (102, 103), [0.5, 1.0], 9),
 }
 FULL_CASES = {
-    # BASELINE.json configs[1] shapes: SD1.5 512x512, N=1 + CFG -> B=2, 64x64 latents, L=77
-    "sd15_512": (SD15, 2, 64, 77, [981], (102, 103), [0.5, 1.0], 11),
+    # BASELINE.json configs[1] shapes: SD1.5 512x512, N=1 + CFG -> B=2, 64x64 latents, L=77; three timesteps
+    # of the 50-step DDIM table (first, middle, last)
+    "sd15_512": (SD15, 2, 64, 77, [981, 501, 1], (102, 103), [0.5, 1.0], 11),
+    # configs[2]: SD2.1 (models/cldm_v21.yaml:21-55) 768x768, N=4 + CFG -> B=8, 96x96 latents, 1 ControlNet
+    "sd21_768": (SD21, 8, 96, 77, [501], (102,), [1.0], 12),
+    # configs[3]: SD1.5 512x512, 4 images per GPU + CFG -> B=8, SAM + inpaint ControlNets
+    "sd15_512_b8": (SD15, 8, 64, 77, [741], (102, 103), [0.5, 1.0], 13),
+    # configs[4]: SD1.5 1024x1024 tile refinement (128x128 latents, 16384 tokens), N=1 + CFG, tile ControlNet
+    "sd15_1024": (SD15, 2, 128, 77, [961], (102,), [1.0], 14),
 }
+# Every row of the batch is independent in the reference networks (GroupNorm is per sample, attention per
+# sample); the big cases are therefore evaluated `chunk` rows at a time - the reference's fp32 attention
+# materialises [rows*heads, T, T] logits (8.6 GB per row at 16384 tokens).
+CHUNK = {"sd21_768": 2, "sd15_1024": 1, "sd15_512_b8": 4}
 UNET_SEED = 101
 
 
@@ -41,14 +52,22 @@ def run_case(name, spec):
     x, ctx, hints = make_inputs(cfg, B, lat, L, in_seed, n_controlnets=len(cn_seeds))
     out = {"meta": dict(name=name, B=B, lat=lat, L=L, timesteps=ts, cn_seeds=list(cn_seeds), scales=scales,
                         in_seed=in_seed, unet_seed=UNET_SEED)}
+    chunk = CHUNK.get(name, B)
     for t in ts:
-        tt = torch.full((B,), t, dtype=torch.long)
-        eps, control = ref_shim.reference_apply_model(unet, cns, x, tt, ctx, hints, scales)
+        eps_rows, control = [], None
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, b0 + chunk)
+            tt = torch.full((x[sl].shape[0],), t, dtype=torch.long)
+            e, c = ref_shim.reference_apply_model(unet, cns, x[sl], tt, ctx[sl], [h[sl] for h in hints], scales)
+            eps_rows.append(e.clone())
+            control = c if control is None else [torch.cat([a, b_]) for a, b_ in zip(control, c)]
+        eps = torch.cat(eps_rows)
         out[f"eps_t{t}"] = eps.clone()
         # the summed, scaled control residuals (what the UNet decoder consumes): keep two of the 13
         if cfg.model_channels <= 64:
             out[f"control0_t{t}"] = control[0].clone().to(torch.float16)
-        out[f"control_mid_t{t}"] = control[-1].clone()
+        # mid residual of the first two rows (fp16 for the full-size cases keeps the fixtures small)
+        out[f"control_mid_t{t}"] = control[-1][:2].clone().to(torch.float32 if cfg.model_channels <= 64 else torch.float16)
         out[f"control_std_t{t}"] = torch.tensor([c.std().item() for c in control])
     torch.save(out, os.path.join(GOLD, name + ".pt"))
     print(name, {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out.items() if k != "meta"})
@@ -104,8 +123,10 @@ def main():
     torch.manual_seed(0)
     if "--full" in sys.argv:
         torch.set_num_threads(os.cpu_count())
+        only = [a for a in sys.argv[1:] if not a.startswith("--")]
         for n, s in FULL_CASES.items():
-            run_case(n, s)
+            if not only or n in only:
+                run_case(n, s)
         return
     for n, s in CASES.items():
         run_case(n, s)

@@ -167,19 +167,32 @@ def timestep_embedding(t, out, *, B, dim):
     return out
 
 
-def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, mask=None,
-                 lat_half_out=None, Nimg, H, W, C_):
+def step_gather(step_counter, n_rows, tables, dsts):
+    _bump()
+    row = max(0, min(int(step_counter.item()), n_rows - 1))
+    for t, d in zip(tables, dsts):
+        d.copy_(t[row].reshape(d.shape))
+
+
+def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, noise=None,
+                 mask=None, lat_half_out=None, step_counter=None, Nimg, H, W, C_):
     _bump()
     eps = F.conv2d(xn.float().permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
     if eps_out is not None:
         eps_out.copy_(eps)
     if latents is not None:
         e = eps[:Nimg] + guidance * (eps[Nimg:] - eps[:Nimg])
-        sa, s1a, sap, s1ap = [float(c) for c in coef]
+        sa, s1a, sap, s1ap = [float(c) for c in coef[:4]]
         x0 = (latents - s1a * e) / sa
         xp = sap * x0 + s1ap * e
         if known is not None:
-            xp = known * mask[..., None] + xp * (1 - mask[..., None])
+            kn, mk = known, mask[..., None]
+            if noise is not None:
+                kn = float(coef[4]) * known + float(coef[5]) * noise
+                mk = mk * float(coef[6])
+            xp = kn * mk + xp * (1 - mk)
+        if step_counter is not None:
+            step_counter += 1
         latents.copy_(xp)
         if lat_half_out is not None:
             lat_half_out.copy_(torch.cat([xp, xp]))

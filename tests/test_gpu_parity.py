@@ -9,13 +9,14 @@ import pytest
 import torch
 
 from editanything_b200.denoise import DenoiseEngine, ddim_schedule
-from editanything_b200.unet_spec import SD15, TINY, TINY21, build_topology, make_state_dict
+from editanything_b200.unet_spec import SD15, SD21, TINY, TINY21, build_topology, make_state_dict
 from oracle import unet_oracle as O
 from oracle.inputs import make_inputs
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CFGS = {"tiny_sd15": TINY, "tiny_sd21": TINY21, "tiny_sd15_32": TINY, "sd15_512": SD15}
+CFGS = {"tiny_sd15": TINY, "tiny_sd21": TINY21, "tiny_sd15_32": TINY, "sd15_512": SD15, "sd21_768": SD21,
+        "sd15_512_b8": SD15, "sd15_1024": SD15}
 EPS_TOL = 1e-2
 
 
@@ -28,6 +29,10 @@ def _engine(name):
     eng = DenoiseEngine(cfg, usd, csds, torch.device("cuda:0"))
     x, ctx, hints = make_inputs(cfg, m["B"], m["lat"], m["L"], m["in_seed"], n_controlnets=len(csds))
     eng.prepare(ctx, hints, m["scales"])
+    if cfg.model_channels > 64:
+        del usd, csds
+        usd = csds = None
+        torch.cuda.empty_cache()
     return g, m, eng, x, (cfg, usd, csds, ctx, hints)
 
 
@@ -41,17 +46,40 @@ def test_eps_vs_reference_golden_reduced_width(name):
         assert err < EPS_TOL, (name, t, err, ref.abs().max().item())
 
 
+def _check_full(name):
+    g, m, eng, x, _ = _engine(name)
+    for t in m["timesteps"]:
+        eps = eng.eps(x, t).cpu()
+        ref = g[f"eps_t{t}"]
+        err = (eps - ref).abs().max().item()
+        rel = ((eps - ref).norm() / ref.norm()).item()
+        print(f"{name} t={t} eps max-abs {err:.3e} rel-fro {rel:.3e} ref-max {ref.abs().max().item():.3f}")
+        assert err < EPS_TOL, (name, t, err, rel)
+
+
 def test_eps_vs_reference_golden_full_sd15_512():
     """BASELINE.json configs[1]: SD1.5, 512x512 (64x64 latents), 1 image + CFG, SAM + inpaint
-    ControlNets, L = 77.  Golden eps was produced by the reference's own cldm modules."""
-    g, m, eng, x, _ = _engine("sd15_512")
-    t = m["timesteps"][0]
-    eps = eng.eps(x, t).cpu()
-    ref = g[f"eps_t{t}"]
-    err = (eps - ref).abs().max().item()
-    rel = ((eps - ref).norm() / ref.norm()).item()
-    print(f"sd15_512 eps max-abs {err:.3e} rel-fro {rel:.3e} ref-max {ref.abs().max().item():.3f}")
-    assert err < EPS_TOL, (err, rel)
+    ControlNets, L = 77, at the first / middle / last timestep of the 50-step DDIM table.  Golden eps
+    was produced by the reference's own cldm modules (oracle/make_golden.py --full)."""
+    _check_full("sd15_512")
+
+
+def test_eps_vs_reference_golden_full_sd21_768_batch4():
+    """BASELINE.json configs[2]: SD2.1 (models/cldm_v21.yaml:21-55: 64-wide heads, linear proj_in/out,
+    ctx 1024), 768x768 (96x96 latents, 9216-token self-attention), N = 4 + CFG => B = 8, 1 ControlNet."""
+    _check_full("sd21_768")
+
+
+def test_eps_vs_reference_golden_full_sd15_512_batch4():
+    """BASELINE.json configs[3] per-GPU shard: SD1.5 512x512, 4 images + CFG => B = 8, SAM + inpaint
+    ControlNets."""
+    _check_full("sd15_512_b8")
+
+
+def test_eps_vs_reference_golden_full_sd15_1024_tile():
+    """BASELINE.json configs[4]: SD1.5 1024x1024 tile refinement (128x128 latents, 16384 tokens at the top
+    level), N = 1 + CFG, one (tile) ControlNet."""
+    _check_full("sd15_1024")
 
 
 def test_eps_vs_cpu_oracle_fresh_inputs():

@@ -230,3 +230,21 @@ def test_full_call_with_the_vae_engine_on_both_sides():
     assert out.shape == ref.shape == (1, 64, 64, 3)
     assert abs(out - ref).max() < 2e-3
 
+
+
+def test_callback_sees_unblended_latents():
+    """The reference calls `callback(i, t, latents)` before the inpaint blend of step i
+    (utils/...inpaint.py:1640-1656); with a callback the blend therefore runs after it, outside the fused step."""
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup()
+    seen = []
+    kw = dict(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+              num_inference_steps=4, guidance_scale=9.0, prompt_embeds=pe, negative_prompt_embeds=ne,
+              output_type="latent", controlnet_conditioning_scale=[0.5, 1.0], alignment_ratio=0.5,
+              num_images_per_prompt=1)
+    a = pipe(generator=torch.manual_seed(7), callback=lambda i, t, x: seen.append(x.clone()), **kw).images
+    b = pipe(generator=torch.manual_seed(7), **kw).images
+    ref = _reference_loop(cfg, usd, csds, image, mask, conds, pe, ne, 4, 9.0, [0.5, 1.0], 7, 0.5)
+    assert len(seen) == 4
+    assert (a - ref).abs().max().item() < 2e-4 and (b - ref).abs().max().item() < 2e-4
+    # step 0's callback latents differ from the blended ones inside the kept region
+    assert (seen[0] - a).abs().max().item() > 1e-3
