@@ -68,6 +68,12 @@ struct GemmKParams {
   int pair_release;  // stages are released to the producer two at a time (even stage count >= 4)
   float* ws;   // [tiles][splits][128][BN] fp32
   int* cnt;    // [tiles][2]: arrived, done (zero between launches)
+  // LayerNorm fold (see ea_gemm_args): producer side / consumer side
+  float2* rowstats_out;     // [N/32][M] (sum, sumsq) of the stored values per 32-column chunk
+  const float2* ln_stats;   // [ln_parts][M] partials of this GEMM's A rows
+  const float* ln_g;        // [N]
+  int ln_parts;
+  float ln_inv_c, ln_eps;
   int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
@@ -192,14 +198,23 @@ __device__ __forceinline__ void residual_load64(uint4 (&rr)[8], const ea_half* r
 }
 
 // GEGLU: value chunk fx (tile columns c..c+31), gate chunk fg (tile columns BN/2+c..): out = x*gelu(g)
+// ln: the LayerNorm fold - acc * rstd[m] - rstd[m] * mean[m] * g[n] + c[n], g staged at cb + 256
 __device__ __forceinline__ void epilogue_geglu32(const float* cb, int half_bn, int c, float (&fx)[32],
-                                                 float (&fg)[32], uint4 (&o)[4]) {
+                                                 float (&fg)[32], uint4 (&o)[4], bool ln, float ln_r,
+                                                 float ln_nm) {
   uint32_t packed[16];
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    const float2 bx = *reinterpret_cast<const float2*>(cb + c + j);
-    const float2 bg = *reinterpret_cast<const float2*>(cb + half_bn + c + j);
-    const float x0 = fx[j] + bx.x, x1 = fx[j + 1] + bx.y, g0 = fg[j] + bg.x, g1 = fg[j + 1] + bg.y;
+    float2 bx = *reinterpret_cast<const float2*>(cb + c + j);
+    float2 bg = *reinterpret_cast<const float2*>(cb + half_bn + c + j);
+    if (ln) {
+      const float2 gx = *reinterpret_cast<const float2*>(cb + 256 + c + j);
+      const float2 gg = *reinterpret_cast<const float2*>(cb + 256 + half_bn + c + j);
+      bx.x = fmaf(ln_nm, gx.x, bx.x); bx.y = fmaf(ln_nm, gx.y, bx.y);
+      bg.x = fmaf(ln_nm, gg.x, bg.x); bg.y = fmaf(ln_nm, gg.y, bg.y);
+    }
+    const float x0 = fmaf(fx[j], ln_r, bx.x), x1 = fmaf(fx[j + 1], ln_r, bx.y);
+    const float g0 = fmaf(fg[j], ln_r, bg.x), g1 = fmaf(fg[j + 1], ln_r, bg.y);
     packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
   }
 #pragma unroll
@@ -564,6 +579,21 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint4 rres[8];   // next 64-column group of the residual (coalesced layout)
     const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
     const bool has_res = p.residual != nullptr;
+    // LayerNorm fold, consumer side: this row's mean / rstd from the producer's per-chunk partials (fixed
+    // summation order: deterministic), while the main loop runs.  out = acc * ln_r + ln_nm * g[n] + c[n].
+    const bool ln = p.ln_stats != nullptr;
+    float ln_r = 1.f, ln_nm = 0.f;
+    if (ln && ri.ok) {
+      float s = 0.f, q = 0.f;
+      for (int j = 0; j < p.ln_parts; ++j) {
+        const float2 v = __ldcg(p.ln_stats + (size_t)j * p.M + ri.m);
+        s += v.x;
+        q += v.y;
+      }
+      const float mu = s * p.ln_inv_c;
+      ln_r = rsqrtf(fmaxf(q * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
+      ln_nm = -ln_r * mu;
+    }
     if (fast) {
       for (int i = et; i < p.BN; i += 128) {
         const int col = ncol0 + i;
@@ -571,7 +601,8 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (col < p.N) {
           const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
           v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
-          v1 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
+          v1 = ln ? __ldg(p.ln_g + col)       // no row vector with the fold: the second slot carries g[n]
+                  : bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
         }
         cb[i] = v0;
         cb[256 + i] = v1;
@@ -579,8 +610,11 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (has_res) residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0, p.BN, p.N, lin_m0, p.M);
       epi_bar_sync();
     } else if (geglu && p.splits == 1) {
-      for (int i = et; i < p.BN; i += 128)
-        cb[i] = (p.bias && ncol0 + i < p.N) ? __ldg(p.bias + ncol0 + i) : 0.f;
+      for (int i = et; i < p.BN; i += 128) {
+        const bool in = ncol0 + i < p.N;
+        cb[i] = (p.bias && in) ? __ldg(p.bias + ncol0 + i) : 0.f;
+        if (ln) cb[256 + i] = in ? __ldg(p.ln_g + ncol0 + i) : 0.f;
+      }
       epi_bar_sync();
     }
     mbar_wait(tmem_full_bar, 0);
@@ -593,7 +627,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint4* stg = reinterpret_cast<uint4*>(smem + wq * 4096);
     uint4* stg2 = reinterpret_cast<uint4*>(smem + 16384 + wq * 4096);   // >= 2 stages of >= 18 KB exist
     if (fast) {
-      const float* cbr = cb + (ri.batch != b_first ? 256 : 0);
+      const float* cbr = cb + ((!ln && ri.batch != b_first) ? 256 : 0);
       // one 32-column chunk: residual hand-off, bias / activation / scale / residual, staging, flush
       auto process = [&](const uint32_t (&v)[32], const int c) {
         const int n_first = ncol0 + c;
@@ -613,13 +647,25 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         {
           float f[32];
+          if (ln) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(cb + c + j);
+              const float4 g4 = *reinterpret_cast<const float4*>(cb + 256 + c + j);
+              f[j] = fmaf(__uint_as_float(v[j]), ln_r, fmaf(ln_nm, g4.x, b4.x));
+              f[j + 1] = fmaf(__uint_as_float(v[j + 1]), ln_r, fmaf(ln_nm, g4.y, b4.y));
+              f[j + 2] = fmaf(__uint_as_float(v[j + 2]), ln_r, fmaf(ln_nm, g4.z, b4.z));
+              f[j + 3] = fmaf(__uint_as_float(v[j + 3]), ln_r, fmaf(ln_nm, g4.w, b4.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
+              f[j] = __uint_as_float(v[j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
           }
           if (p.act == EA_ACT_SILU) {
 #pragma unroll
@@ -643,6 +689,16 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             stg[slot] = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
                                    ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
+          }
+          if (p.rowstats_out) {
+            // LayerNorm fold, producer side: this row's (sum, sum of squares) over the chunk's 32 stored values
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              s0 += f[j]; q0 = fmaf(f[j], f[j], q0);
+              s1 += f[j + 1]; q1 = fmaf(f[j + 1], f[j + 1], q1);
+            }
+            if (ri.ok && n_first < p.N) p.rowstats_out[(size_t)(n_first >> 5) * p.M + ri.m] = make_float2(s0 + s1, q0 + q1);
           }
         }
         if (half == 1 || c + 32 >= p.BN)
@@ -674,7 +730,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
           uint4 o[4];
-          epilogue_geglu32(cb, half_bn, c, fx, fg, o);
+          epilogue_geglu32(cb, half_bn, c, fx, fg, o, ln, ln_r, ln_nm);
           const int half = (c >> 5) & 1;
           stage_put32(stg, lane, half, o);
           if (half == 1 || c + 32 >= half_bn)
@@ -1052,6 +1108,20 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
       const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
       const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
       uint4 rres[8];
+      // LayerNorm fold, consumer side (see ea_gemm_kernel)
+      const bool ln = p.ln_stats != nullptr;
+      float ln_r = 1.f, ln_nm = 0.f;
+      if (ln && ri.ok) {
+        float s = 0.f, q = 0.f;
+        for (int j = 0; j < p.ln_parts; ++j) {
+          const float2 v = __ldcg(p.ln_stats + (size_t)j * p.M + ri.m);
+          s += v.x;
+          q += v.y;
+        }
+        const float mu = s * p.ln_inv_c;
+        ln_r = rsqrtf(fmaxf(q * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
+        ln_nm = -ln_r * mu;
+      }
       if (!geglu) {
         for (int i = et; i < p.BN; i += EPI_THREADS) {
           const int col = ncol0 + i;
@@ -1059,7 +1129,8 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           if (col < p.N) {
             const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
             v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
-            v1 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
+            v1 = ln ? __ldg(p.ln_g + col)
+                    : bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
           }
           cbt[i] = v0;
           cbt[256 + i] = v1;
@@ -1067,15 +1138,18 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
         if (has_res && wg * 64 < p.BN)
           residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
       } else {
-        for (int i = et; i < p.BN; i += EPI_THREADS)
-          cbt[i] = (p.bias && ncol0 + i < p.N) ? __ldg(p.bias + ncol0 + i) : 0.f;
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
+          const bool in = ncol0 + i < p.N;
+          cbt[i] = (p.bias && in) ? __ldg(p.bias + ncol0 + i) : 0.f;
+          if (ln) cbt[256 + i] = in ? __ldg(p.ln_g + ncol0 + i) : 0.f;
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[abuf], fphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)abuf * acc_cols;
       if (!geglu) {
-        const float* cbr = cbt + (ri.batch != b_first ? 256 : 0);
+        const float* cbr = cbt + ((!ln && ri.batch != b_first) ? 256 : 0);
         // this warp-group's chunks: both halves of the 64-column groups wg, wg + EPI_WG, ...; the next chunk's
         // tcgen05.ld is in flight while the current one is converted and stored
         uint32_t va[32], vb[32];
@@ -1102,13 +1176,25 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           }
           {
             float f[32];
+            if (ln) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
-              f[j] = __uint_as_float(va[j]) + b4.x;
-              f[j + 1] = __uint_as_float(va[j + 1]) + b4.y;
-              f[j + 2] = __uint_as_float(va[j + 2]) + b4.z;
-              f[j + 3] = __uint_as_float(va[j + 3]) + b4.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(cbt + c + j);
+                const float4 g4 = *reinterpret_cast<const float4*>(cbt + 256 + c + j);
+                f[j] = fmaf(__uint_as_float(va[j]), ln_r, fmaf(ln_nm, g4.x, b4.x));
+                f[j + 1] = fmaf(__uint_as_float(va[j + 1]), ln_r, fmaf(ln_nm, g4.y, b4.y));
+                f[j + 2] = fmaf(__uint_as_float(va[j + 2]), ln_r, fmaf(ln_nm, g4.z, b4.z));
+                f[j + 3] = fmaf(__uint_as_float(va[j + 3]), ln_r, fmaf(ln_nm, g4.w, b4.w));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
+                f[j] = __uint_as_float(va[j]) + b4.x;
+                f[j + 1] = __uint_as_float(va[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(va[j + 2]) + b4.z;
+                f[j + 3] = __uint_as_float(va[j + 3]) + b4.w;
+              }
             }
             if (p.act == EA_ACT_SILU) {
 #pragma unroll
@@ -1133,6 +1219,15 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
               stg[slot] = make_uint4(ea_pack2(f[q * 8 + 0], f[q * 8 + 1]), ea_pack2(f[q * 8 + 2], f[q * 8 + 3]),
                                      ea_pack2(f[q * 8 + 4], f[q * 8 + 5]), ea_pack2(f[q * 8 + 6], f[q * 8 + 7]));
             }
+            if (p.rowstats_out) {   // LayerNorm fold, producer side
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                s0 += f[j]; q0 = fmaf(f[j], f[j], q0);
+                s1 += f[j + 1]; q1 = fmaf(f[j + 1], f[j + 1], q1);
+              }
+              if (ri.ok && n_first < p.N) p.rowstats_out[(size_t)(n_first >> 5) * p.M + ri.m] = make_float2(s0 + s1, q0 + q1);
+            }
           }
           if (half == 1 || c + 32 >= p.BN)
             stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
@@ -1149,7 +1244,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
           uint4 o[4];
-          epilogue_geglu32(cbt, half_bn, c, fx, fg, o);
+          epilogue_geglu32(cbt, half_bn, c, fx, fg, o, ln, ln_r, ln_nm);
           const int half = (c >> 5) & 1;
           stage_put32(stg, lane, half, o);
           if (half == 1 || c + 32 >= half_bn)
@@ -1167,7 +1262,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) { fx[j] = __uint_as_float(xv[j]); fg[j] = __uint_as_float(gv[j]); }
           uint4 o[4];
-          epilogue_geglu32(cbt, half_bn, c, fx, fg, o);
+          epilogue_geglu32(cbt, half_bn, c, fx, fg, o, ln, ln_r, ln_nm);
           stage_put32(stg, lane, 0, o);
           stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c, 4, p.N >> 1, lin_m0, p.M);
         }
@@ -1312,6 +1407,15 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
       }
     }
   }
+  // Measured deviations from the cost model (profiles/r01r_exp_splitk_sweep.txt, B200, 148 SMs): two shapes of the
+  // 16x16 level where a sweep over (BN, splits) beat the model's pick by 13-14 %.
+  if (ws_floats > 0 && mt == 4 && N == 1280 && act != EA_ACT_GEGLU) {
+    if (nkb == 80 && best.splits > 1)                       // ff2: 512 x 1280, K = 5120: 24.1 vs 28.0 us
+      best = {64, 8, 1, nkb, 1, best.cost, 0};
+    else if (nkb >= 360 && nkb <= 400 && best.BN == 256 &&  // conv 2560 -> 1280 (+ 1x1 skip): 45.5 vs 52.5 us
+             4LL * mt * 8 * (BM * 160) <= ws_floats)
+      best = {160, 6, 4, (nkb + 3) / 4, 1, best.cost, 0};
+  }
   return best;
 }
 
@@ -1391,6 +1495,18 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   p.act = a->act;
   p.out_scale = a->out_scale;
   p.accumulate = a->accumulate;
+  const bool ln_any = a->rowstats_out || a->ln_stats;
+  if (ln_any) {
+    if (a->mode != EA_GEMM_LINEAR || a->rowvec || a->out_f32 || a->accumulate) return EA_ERR_ARG;
+    if (a->rowstats_out && (a->N % 32 != 0 || a->act == EA_ACT_GEGLU)) return EA_ERR_SHAPE;
+    if (a->ln_stats && (!a->ln_g || a->ln_parts <= 0 || a->K != a->ln_parts * 32)) return EA_ERR_ARG;
+    p.rowstats_out = reinterpret_cast<float2*>(a->rowstats_out);
+    p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+    p.ln_g = a->ln_g;
+    p.ln_parts = a->ln_parts;
+    p.ln_inv_c = a->ln_stats ? 1.0f / (float)a->K : 0.f;
+    p.ln_eps = a->ln_eps;
+  }
   if (p.ldo % 8 != 0 || (p.residual && p.ldr % 8 != 0) || (p.out2 && p.ldo2 % 8 != 0))
     return EA_ERR_SHAPE;
 
@@ -1456,12 +1572,14 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   }
   const int nkb = p.nkb_main + p.nkb_extra;
   // workspace: [0, 64 KB) arrival counters (int, zero between launches), then fp32 partial tiles
-  const long long ws_floats =
-      (a->workspace && a->workspace_bytes > 65536) ? (a->workspace_bytes - 65536) / 4 : 0;
+  const long long ws_floats =      // the LayerNorm fold lives in the unsplit epilogues only
+      (a->workspace && a->workspace_bytes > 65536 && !ln_any) ? (a->workspace_bytes - 65536) / 4 : 0;
   static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
   const bool can_two = a->mode != EA_GEMM_CONV_S2 && a->mode != EA_GEMM_CONV_S2A && two_env != 0 && a->force_2cta >= 0;
   // Persistent variant (experimental): wanted when forced, or with EA_GEMM_PERSIST=1 for multi-wave grids.
-  static const int persist_env = [] { const char* e = getenv("EA_GEMM_PERSIST"); return e ? atoi(e) : 0; }();
+  // EA_GEMM_PERSIST: unset / 3 = per-launch choice (below), 0 = never, 1 / 2 = wherever the launch qualifies
+  // (4 / 8 epilogue warps; the A/B switches of profiles/r02a_gemm_breakdown_*).
+  static const int persist_env = [] { const char* e = getenv("EA_GEMM_PERSIST"); return e ? atoi(e) : 3; }();
   const bool batch_ok =
       !a->rowvec || (a->mode == EA_GEMM_LINEAR
                          ? (a->rows_per_batch == 0 || a->rows_per_batch >= BM || a->rows_per_batch == BM / 2)
@@ -1469,7 +1587,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   const bool persist_ok = !a->out_f32 && !a->accumulate && a->force_splits <= 1 && a->force_2cta <= 0 &&
                           (a->act == EA_ACT_GEGLU || batch_ok);
   bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
-  const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env == 2)) ? 2 : 1;
+  const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env >= 2)) ? 2 : 1;
   GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
   if (persist && a->force_persistent == 0) {
     // auto mode (environment switch): never where the planner splits K (weight-streaming small-M layers; first
@@ -1478,6 +1596,16 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
     // the epilogue of a single tile)
     const long long tiles0 = (long long)m_tiles * ((a->N + plan.BN - 1) / plan.BN);
     if (plan.splits > 1 || (persist_wg == 1 && tiles0 <= sm_count())) persist = false;
+    if (persist && persist_env == 3) {
+      // Default: the 8-epilogue-warp persistent kernel wherever its tile list balances over the SMs - at most one
+      // wave, or at least two.  Measured per shape on B200 (profiles/r02a_gemm_breakdown_{base,persist2}.json): it
+      // wins 7-27 % on the GEGLU projections, the C x C linears of the 32x32 / 16x16 levels and the long-K
+      // convolutions (sum over a step's 362 launches 6.16 -> 5.86 ms), and loses 6-20 % where 148 < tiles < 296
+      // leaves half the SMs a second tile to do alone (64 x 4 tiles: 8192 x 320 x 320, 8192 x 640 x 5760).
+      const GemmPlan pp = plan.two ? plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, a->residual != nullptr) : plan;
+      const long long tiles_p = (long long)m_tiles * ((a->N + pp.BN - 1) / pp.BN);
+      if (tiles_p > sm_count() && tiles_p < 2LL * sm_count()) persist = false;
+    }
   }
   if (persist && (plan.two || plan.splits > 1))   // the persistent kernel has no CTA pairs and no split-K
     plan = plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, a->residual != nullptr);
@@ -1501,6 +1629,7 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
     }
     if (a->force_2cta <= 0 && (a->force_bn > 0 || a->force_splits > 0)) plan.two = 0;
   }
+  if (ln_any && plan.splits > 1) return EA_ERR_ARG;
   const int two = plan.two && plan.splits == 1 && plan.BN >= 64 && plan.BN % 32 == 0;
   p.BN = plan.BN;
   if (p.BN < 32 || p.BN > 256 || p.BN % 32 != 0) return EA_ERR_ARG;

@@ -15,6 +15,8 @@ Reference semantics followed (paths relative to the reference root):
     SpatialTransformer.forward    ldm/modules/attention.py:321-340
     BasicTransformerBlock         ldm/modules/attention.py:271-275
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -43,6 +45,9 @@ class PackedNet:
     def __init__(self, cfg: UNetConfig, kind: str, state_dict, device, backend=None):
         self.cfg, self.kind = cfg, kind
         self.ops = backend or _cuda_ops
+        # LayerNorm folded into the GEMMs around it (ea_gemm_args.rowstats_out / ln_*): no LayerNorm launch, no
+        # normalised tensor.  EA_LN_FOLD=0 keeps the separate ea_layernorm launches (A/B, debugging).
+        self.ln_fold = os.environ.get("EA_LN_FOLD", "1") != "0"
         self.dev = device
         self.hdt = self.ops.half_dtype()
         self.topo = build_topology(cfg, with_decoder=(kind == "unet"))
@@ -122,15 +127,25 @@ class PackedNet:
         self.w[p + ".proj_in.b"] = F(sd[p + ".proj_in.bias"])
         self.w[p + ".proj_out.w"] = H(sd[p + ".proj_out.weight"].reshape(c, inner))
         self.w[p + ".proj_out.b"] = F(sd[p + ".proj_out.bias"])
-        self.w[p + ".qkv1.w"] = H(torch.cat([sd[f"{tb}.attn1.to_q.weight"], sd[f"{tb}.attn1.to_k.weight"],
-                                             sd[f"{tb}.attn1.to_v.weight"]], 0))
+        qkv1 = torch.cat([sd[f"{tb}.attn1.to_q.weight"], sd[f"{tb}.attn1.to_k.weight"], sd[f"{tb}.attn1.to_v.weight"]], 0)
+        q2 = sd[f"{tb}.attn2.to_q.weight"]
+        idx = _geglu_interleave(inner * 4)
+        ff1, ff1b = sd[f"{tb}.ff.net.0.proj.weight"][idx], sd[f"{tb}.ff.net.0.proj.bias"][idx]
+        if self.ln_fold:
+            # LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * g) + (W beta + b)   (attention.py:263-275)
+            for name, wt, bt, nrm in (("qkv1", qkv1, None, "norm1"), ("q2", q2, None, "norm2"), ("ff1", ff1, ff1b, "norm3")):
+                gam, bet = sd[f"{tb}.{nrm}.weight"].double(), sd[f"{tb}.{nrm}.bias"].double()
+                wg = H((wt.double() * gam[None, :]).float())
+                self.w[f"{p}.{name}.w"] = wg
+                self.w[f"{p}.{name}.g"] = F(wg.double().sum(1).float())     # of the ROUNDED weights: exact cancellation
+                c = wt.double() @ bet
+                self.w[f"{p}.{name}.b"] = F((c + bt.double() if bt is not None else c).float())
+        else:
+            self.w[p + ".qkv1.w"], self.w[p + ".q2.w"] = H(qkv1), H(q2)
+            self.w[p + ".ff1.w"], self.w[p + ".ff1.b"] = H(ff1), F(ff1b)
         self.w[p + ".o1.w"], self.w[p + ".o1.b"] = H(sd[f"{tb}.attn1.to_out.0.weight"]), F(sd[f"{tb}.attn1.to_out.0.bias"])
-        self.w[p + ".q2.w"] = H(sd[f"{tb}.attn2.to_q.weight"])
         self.w[p + ".kv2.w"] = H(torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], 0))
         self.w[p + ".o2.w"], self.w[p + ".o2.b"] = H(sd[f"{tb}.attn2.to_out.0.weight"]), F(sd[f"{tb}.attn2.to_out.0.bias"])
-        idx = _geglu_interleave(inner * 4)
-        self.w[p + ".ff1.w"] = H(sd[f"{tb}.ff.net.0.proj.weight"][idx])
-        self.w[p + ".ff1.b"] = F(sd[f"{tb}.ff.net.0.proj.bias"][idx])
         self.w[p + ".ff2.w"], self.w[p + ".ff2.b"] = H(sd[f"{tb}.ff.net.2.weight"]), F(sd[f"{tb}.ff.net.2.bias"])
         for n in ("norm1", "norm2", "norm3"):
             self.w[f"{p}.{n}.g"], self.w[f"{p}.{n}.b"] = F(sd[f"{tb}.{n}.weight"]), F(sd[f"{tb}.{n}.bias"])
@@ -225,28 +240,35 @@ class PackedNet:
         xn = self._new(B, H, W_, c)
         o.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], xn, B=B, HW=N, C_=c, eps=1e-6, silu=False,
                     workspace=gn_ws, ldx=x.stride(2))
-        t0 = o.gemm(xn.view(M, c), w[p + ".proj_in.w"], bias=w[p + ".proj_in.b"])
-        n1 = self._new(M, inner)
-        o.layernorm(t0, w[p + ".norm1.g"], w[p + ".norm1.b"], n1, M=M, C_=inner)
-        qkv = o.gemm(n1, w[p + ".qkv1.w"])                       # [M, 3*inner]
+        fold = self.ln_fold
+
+        def stats():   # per-row partial (sum, sumsq) per 32-column chunk, written by the producing GEMM
+            return torch.empty(inner // 32, M, 2, device=self.dev, dtype=torch.float32) if fold else None
+
+        def normed(t, st, name, nrm, **kw):   # GEMM on LayerNorm(t): folded, or LayerNorm launch + plain GEMM
+            if fold:
+                return o.gemm(t, w[f"{p}.{name}.w"], bias=w[f"{p}.{name}.b"], ln=(st, w[f"{p}.{name}.g"], 1e-5), **kw)
+            n = self._new(M, inner)
+            o.layernorm(t, w[f"{p}.{nrm}.g"], w[f"{p}.{nrm}.b"], n, M=M, C_=inner)
+            return o.gemm(n, w[f"{p}.{name}.w"], bias=w.get(f"{p}.{name}.b"), **kw)
+
+        st0, st1, st2 = stats(), stats(), stats()
+        t0 = o.gemm(xn.view(M, c), w[p + ".proj_in.w"], bias=w[p + ".proj_in.b"], rowstats_out=st0)
+        qkv = normed(t0, st0, "qkv1", "norm1")                  # [M, 3*inner]
         ao = self._new(M, inner)
         o.attention(qkv, qkv[:, inner:], qkv[:, 2 * inner:], ao, B=B, heads=heads, Nq=N, Nkv=N, d=dh,
                     q_strides=(N * 3 * inner, 3 * inner), k_strides=(N * 3 * inner, 3 * inner),
                     v_strides=(N * 3 * inner, 3 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
-        t1 = o.gemm(ao, w[p + ".o1.w"], bias=w[p + ".o1.b"], residual=t0)
-        n2 = self._new(M, inner)
-        o.layernorm(t1, w[p + ".norm2.g"], w[p + ".norm2.b"], n2, M=M, C_=inner)
-        q2 = o.gemm(n2, w[p + ".q2.w"])
+        t1 = o.gemm(ao, w[p + ".o1.w"], bias=w[p + ".o1.b"], residual=t0, rowstats_out=st1)
+        q2 = normed(t1, st1, "q2", "norm2")
         kv = ctxc["kv"][p]
         Lc = ctxc["L"]
         ao2 = self._new(M, inner)
         o.attention(q2, kv, kv[:, inner:], ao2, B=B, heads=heads, Nq=N, Nkv=Lc, d=dh,
                     q_strides=(N * inner, inner), k_strides=(Lc * 2 * inner, 2 * inner),
                     v_strides=(Lc * 2 * inner, 2 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
-        t2 = o.gemm(ao2, w[p + ".o2.w"], bias=w[p + ".o2.b"], residual=t1)
-        n3 = self._new(M, inner)
-        o.layernorm(t2, w[p + ".norm3.g"], w[p + ".norm3.b"], n3, M=M, C_=inner)
-        g = o.gemm(n3, w[p + ".ff1.w"], bias=w[p + ".ff1.b"], act=L.EA_ACT_GEGLU)   # [M, 4*inner]
+        t2 = o.gemm(ao2, w[p + ".o2.w"], bias=w[p + ".o2.b"], residual=t1, rowstats_out=st2)
+        g = normed(t2, st2, "ff1", "norm3", act=L.EA_ACT_GEGLU)   # [M, 4*inner]
         t3 = o.gemm(g, w[p + ".ff2.w"], bias=w[p + ".ff2.b"], residual=t2)
         if out is None:
             out = self._new(B, H, W_, c)

@@ -61,8 +61,10 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
          conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
          out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
          ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0,
-         force_persistent=0):
-    """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes."""
+         force_persistent=0, rowstats_out=None, ln=None):
+    """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes.
+    rowstats_out: fp32 [N/32, M, 2] per-row partial (sum, sumsq) of the stored values (LayerNorm fold, producer);
+    ln = (stats [K/32, M, 2], g [N], eps): the consumer side - `w` is W*gamma, `bias` is W beta + b."""
     lib = L.lib()
     g = L.GemmArgs()
     g.mode = mode
@@ -113,6 +115,11 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     g.force_2cta = force_2cta
     g.force_persistent = force_persistent
     g.no_spin = 1 if _CONCURRENT[0] else 0
+    if rowstats_out is not None:
+        g.rowstats_out = rowstats_out.data_ptr()
+    if ln is not None:
+        stats, lg, eps = ln
+        g.ln_stats, g.ln_g, g.ln_parts, g.ln_eps = stats.data_ptr(), lg.data_ptr(), stats.shape[0], eps
     ws = gemm_workspace(a.device)
     g.workspace = ws.data_ptr()
     g.workspace_bytes = ws.numel()

@@ -112,6 +112,19 @@ typedef struct ea_gemm_args {
                                 (one CTA per SM walks the tile list with two TMEM accumulators: EXPERIMENTAL,
                                 see DESIGN.md section 8) when the launch qualifies; 2 = the same with eight
                                 epilogue warps (two per SM sub-partition); -1 = never */
+  /* LayerNorm folded into the GEMMs around it (BasicTransformerBlock norm1/2/3, ldm/modules/attention.py:
+   * 263-275): LN(x) W^T = rstd[m] * (x (W*gamma)^T - mean[m] * g) + (W beta + b), g[n] = sum_k (W*gamma)[n,k].
+   * The GEMM that PRODUCES x (proj_in / to_out + residual) also writes per-row partial statistics of the
+   * values it stores, one (sum, sum of squares) pair per 32-column chunk: rowstats_out fp32 [N/32][M][2]
+   * (deterministic: no atomics).  The GEMM that CONSUMES x (to_q/k/v, GEGLU proj) takes W*gamma as `w`,
+   * W beta + b as `bias`, and ln_stats (= the producer's rowstats_out, ln_parts = K/32 chunks), ln_g, ln_eps:
+   * its epilogue applies rstd / mean per output row.  LINEAR mode, no rowvec / out_f32 / accumulate, N % 32 == 0
+   * for the producer; K is never split for either.  No LayerNorm launch and no normalised tensor exists. */
+  float* rowstats_out;
+  const float* ln_stats;
+  const float* ln_g;         /* fp32 [N] */
+  int ln_parts;
+  float ln_eps;
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K

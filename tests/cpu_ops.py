@@ -33,13 +33,19 @@ def _bump(n=1):
 def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, conv=None, a_extra=None,
          bias=None, rowvec=None, rows_per_batch=0, residual=None, out2=None, out_f32=None, act=0,
          out_scale=1.0, accumulate=False, ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0,
-         force_stages=0, force_splits=0, force_2cta=0, force_persistent=0):
+         force_stages=0, force_splits=0, force_2cta=0, force_persistent=0, rowstats_out=None, ln=None):
     _bump()
     Nn = w.shape[0]
     if mode == EA_GEMM_LINEAR:
         A = a.reshape(-1, a.shape[-1]).float()
         y = A @ w.float().t()
         batch_rows = rows_per_batch
+        if ln is not None:      # LayerNorm fold: rstd * (x W'^T - mean * g) (+ bias below), stats from the producer
+            stats, g, eps = ln
+            sq = stats.float().sum(0)                                   # [M, 2]
+            mu = sq[:, 0] / A.shape[1]
+            rstd = torch.rsqrt((sq[:, 1] / A.shape[1] - mu * mu).clamp_min(0) + eps)
+            y = rstd[:, None] * (y - mu[:, None] * g[None, :])
     else:
         B, H, W_, Cin = conv
         x = a.float().reshape(B, -1, a.shape[-2] if a.dim() == 4 else (W_ if mode == EA_GEMM_CONV_S1 else 2 * W_), Cin).permute(0, 3, 1, 2)
@@ -76,6 +82,9 @@ def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, con
     tgt.copy_(y.reshape(tgt.shape))
     if out2 is not None:
         out2.copy_(y.reshape(out2.shape))
+    if rowstats_out is not None:
+        yc = y.reshape(y.shape[0], -1, 32)
+        rowstats_out.copy_(torch.stack([yc.sum(-1), (yc * yc).sum(-1)], -1).permute(1, 0, 2))
     return tgt
 
 

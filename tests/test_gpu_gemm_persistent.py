@@ -1,19 +1,14 @@
-"""-m gpu, EXPERIMENTAL (runs only with EA_TEST_EXPERIMENTAL=1): the persistent GEMM variant
-(ea_gemm_args.force_persistent = 1) against the validated one-tile-per-CTA
-kernel on the same inputs.  Both compute every output element with the same K order in fp32, so the results
+"""-m gpu: the persistent GEMM variant (ea_gemm_args.force_persistent = 1 | 2; the default for launches whose
+tile list balances over the SMs) against the one-tile-per-CTA kernel on the same inputs.  Both compute every output element with the same K order in fp32, so the results
 must agree to the last bit; grids are chosen to give every CTA several tiles (both TMEM accumulators, barrier
 phase wrap-around) and a ragged last wave."""
-import os
-
 import pytest
 import torch
 
 from editanything_b200 import _lib as L
 from editanything_b200 import ops
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EA_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental kernel: set EA_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _pair(fn):

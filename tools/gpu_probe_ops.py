@@ -511,6 +511,117 @@ def case_out_cfg_ddim():
     return r
 
 
+def _ln_fold_case(M, C, N, geglu, persistent, seed=21):
+    """LayerNorm folded into the GEMMs around it: producer (x = a w0^T + b0 + res, row statistics) ->
+    consumer (LN(x) w1^T + b1, optionally GEGLU) against torch fp32 on the same half inputs."""
+    import torch
+    import torch.nn.functional as F
+    from editanything_b200 import ops, _lib as L
+    dt = ops.half_dtype()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, C, device="cuda", generator=g).to(dt)
+    w0 = (torch.randn(C, C, device="cuda", generator=g) / C ** 0.5).to(dt)
+    b0 = torch.randn(C, device="cuda", generator=g)
+    res = (torch.randn(M, C, device="cuda", generator=g) * 2 + 0.7).to(dt)     # non-zero row means
+    gam = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    bet = 0.3 * torch.randn(C, device="cuda", generator=g)
+    w1 = torch.randn(N, C, device="cuda", generator=g) / C ** 0.5
+    b1 = torch.randn(N, device="cuda", generator=g)
+    # pack like nets.PackedNet._pack_attn
+    wg = (w1.double() * gam.double()[None, :]).float().to(dt)
+    gvec = wg.double().sum(1).float()
+    cvec = (w1.double() @ bet.double()).float() + b1
+    fp = persistent
+    x = torch.full((M, C), 7.0, device="cuda", dtype=dt)
+    st = torch.full((C // 32, M, 2), float("nan"), device="cuda")
+    ops.gemm(a, w0, x, bias=b0, residual=res, rowstats_out=st, force_persistent=fp)
+    out = ops.gemm(x, wg, bias=cvec, ln=(st, gvec, 1e-5), act=L.EA_ACT_GEGLU if geglu else L.EA_ACT_NONE,
+                   force_persistent=fp)
+    torch.cuda.synchronize()
+    xr = x.float()                                     # what the consumer really read
+    x_ref = a.float() @ w0.float().t() + b0 + res.float()
+    y = F.layer_norm(xr, (C,), gam, bet, 1e-5) @ w1.t() + b1
+    if geglu:
+        y = y.reshape(M, N // 128, 2, 64)
+        y = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(M, N // 2)
+    st_ref = torch.stack([x_ref.reshape(M, C // 32, 32).sum(-1), (x_ref ** 2).reshape(M, C // 32, 32).sum(-1)], -1).permute(1, 0, 2)
+    r = {"x": _err(x, x_ref), "stats": _err(st, st_ref), "out": _err(out, y)}
+    # the consumer multiplies fp16(W*gamma) while the reference rounds nothing: allow that extra rounding
+    r["max_abs"] = max(r["x"]["max_abs"], r["out"]["max_abs"] / 2, r["stats"]["max_abs"] / 50)
+    r["ref_max"] = max(1.0, y.abs().max().item() / 2)
+    r["rel_fro"] = max(r["out"]["rel_fro"], r["stats"]["rel_fro"]) / 2
+    return r
+
+
+def case_ln_fold_linear():
+    return _ln_fold_case(2048, 640, 1920, False, -1)
+
+
+def case_ln_fold_linear_ragged():
+    return _ln_fold_case(300, 320, 960, False, -1, seed=22)
+
+
+def case_ln_fold_geglu():
+    return _ln_fold_case(2048, 640, 5120, True, -1, seed=23)
+
+
+def case_ln_fold_linear_persistent():
+    return _ln_fold_case(2048, 640, 1920, False, 2, seed=24)
+
+
+def case_ln_fold_geglu_persistent():
+    return _ln_fold_case(8192, 320, 2560, True, 2, seed=25)
+
+
+def case_ln_fold_geglu_persistent4():
+    return _ln_fold_case(2048, 1280, 10240, True, 1, seed=26)
+
+
+def case_step_gather_and_renoised_blend():
+    """ea_step_gather (row *ctr of every table -> fixed buffers) and the re-noised, per-step gated inpaint blend
+    + step counter of ea_out_cfg_ddim (utils/stable_diffusion_controlnet_inpaint.py:1647-1656)."""
+    import torch
+    import torch.nn.functional as F
+    from editanything_b200 import ops
+    dt = ops.half_dtype()
+    torch.manual_seed(10)
+    Nimg, H, C_ = 2, 16, 320
+    tab_c = torch.rand(5, 8, device="cuda") * 0.5 + 0.3
+    tab_c[:, 6] = torch.tensor([1.0, 1.0, 0.0, 1.0, 0.0])
+    tab_e = torch.randn(5, 2, 1000, device="cuda")
+    tab_f = torch.randn(5, 3, 37, device="cuda")
+    coef, e_buf, f_buf = torch.zeros(8, device="cuda"), torch.zeros(2, 1000, device="cuda"), torch.zeros(3, 37, device="cuda")
+    ctr = torch.zeros(1, device="cuda", dtype=torch.int32)
+    xn = torch.randn(2 * Nimg, H, H, C_, device="cuda").to(dt)
+    w = torch.randn(4, C_, 3, 3, device="cuda") / (9 * C_) ** 0.5
+    b = torch.randn(4, device="cuda")
+    lat = torch.randn(Nimg, H, H, 4, device="cuda")
+    ref = lat.clone()
+    known, noise = torch.randn(Nimg, H, H, 4, device="cuda"), torch.randn(Nimg, H, H, 4, device="cuda")
+    mask = (torch.rand(Nimg, H, H, device="cuda") > 0.5).float()
+    eps = F.conv2d(xn.float().permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    e = eps[:Nimg] + 7.0 * (eps[Nimg:] - eps[:Nimg])
+    worst = 0.0
+    for i in range(7):                    # two steps past the table: the row index clamps to the last row
+        ops.step_gather(ctr, 5, [tab_c, tab_e, tab_f], [coef, e_buf, f_buf])
+        ops.out_cfg_ddim(xn, w.permute(0, 2, 3, 1).contiguous(), b, latents=lat, coef=coef, guidance=7.0, known=known,
+                         noise=noise, mask=mask, step_counter=ctr, Nimg=Nimg, H=H, W=H, C_=C_)
+        torch.cuda.synchronize()
+        r_ = min(i, 4)
+        c = tab_c[r_]
+        x0 = (ref - c[1] * e) / c[0]
+        xp = c[2] * x0 + c[3] * e
+        mk = mask[..., None] * c[6]
+        ref = (c[4] * known + c[5] * noise) * mk + xp * (1 - mk)
+        ref = ref.clamp(-50, 50)
+        lat.clamp_(-50, 50)
+        assert int(ctr.item()) == i + 1
+        assert torch.equal(coef, tab_c[r_]) and torch.equal(e_buf, tab_e[r_]) and torch.equal(f_buf, tab_f[r_])
+        worst = max(worst, ((lat - ref).abs().max() / ref.abs().max().clamp_min(1)).item())
+        lat.copy_(ref)
+    return {"max_abs": worst / 10, "ref_max": 1.0}
+
+
 def case_sam_helpers():
     import torch
     from editanything_b200 import ops
