@@ -71,6 +71,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(cfg, B, lat, L, seed):
+    """B = 2 * images (CFG halves: [uncond x n; cond x n])."""
     """Same synthetic inputs as oracle/inputs.py (SURVEY.md §8d); duplicated here so the product arm
     imports nothing from oracle/."""
     g = torch.Generator().manual_seed(seed)
@@ -115,28 +116,46 @@ class GemmProbe:
     def __getattr__(self, n):
         return getattr(self._ops, n)
 
-    def gemm(self, a, w, out=None, **kw):
-        r = self._ops.gemm(a, w, out, **kw)
+    @staticmethod
+    def _flops(a, w, kw):
         conv = kw.get("conv")
         M = conv[0] * conv[1] * conv[2] if conv else (kw.get("M") or a.shape[0])
+        return 2.0 * M * w.shape[0] * w.shape[1]
+
+    def gemm(self, a, w, out=None, **kw):
+        r = self._ops.gemm(a, w, out, **kw)
         kw2 = dict(kw)
         if out is None and kw.get("out_f32") is None:
             out = r
-        self.records.append((a, w, out, kw2, 2.0 * M * w.shape[0] * w.shape[1]))
+        self.records.append((a, w, out, kw2, self._flops(a, w, kw)))
         return r
+
+    def gemm_grouped(self, calls):
+        """One launch for several networks (ea_gemm_grouped): recorded as ONE launch carrying every group's FLOPs."""
+        outs = self._ops.gemm_grouped(calls)
+        calls2 = [(a, w, o if o is not None else r, dict(kw)) for (a, w, o, kw), r in zip(calls, outs)]
+        self.records.append(("grouped", calls2, None, None, sum(self._flops(a, w, kw) for a, w, _, kw in calls2)))
+        return outs
+
+    def _issue(self, rec):
+        if rec[0] == "grouped":
+            self._ops.gemm_grouped(rec[1])
+        else:
+            a, w, out, kw, _ = rec
+            self._ops.gemm(a, w, out, **kw)
 
     def replay_time_ms(self, reps=3):
         ops = self._ops
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for a, w, out, kw, _ in self.records:
-                ops.gemm(a, w, out, **kw)
+            for rec in self.records:
+                self._issue(rec)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for a, w, out, kw, _ in self.records:
-                ops.gemm(a, w, out, **kw)
+            for rec in self.records:
+                self._issue(rec)
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -146,6 +165,40 @@ class GemmProbe:
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
+
+
+def _all_gather_list(t, world):
+    import torch.distributed as dist
+    bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(bufs, t.contiguous())
+    return bufs
+
+
+def measure_batch_block(eng, cfg, n_img, rank, sust, args, ts, a, ap):
+    """Device-timed fused steps at n_img images per GPU (BASELINE.json configs[3] = 4 per GPU => B = 8), same
+    engine and weights: returns the `config.batchN` block."""
+    x, ctx, hints = make_inputs(cfg, 2 * n_img, 64, 77, 31 + rank)
+    eng.prepare(ctx, hints, [0.5, 1.0])
+    eng.set_schedule(ts, a, ap)
+    eng.begin(x[:n_img], guidance=9.0, use_graph=not args.no_graph)
+    for _ in range(3):
+        eng.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 10
+    e0.record()
+    for _ in range(k):
+        eng.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    tf = STEP_TFLOP * n_img
+    return {"images_per_gpu": n_img, "network_batch": 2 * n_img, "ms_per_step": round(ms, 4), "steps_timed": k,
+            "step_tflop": round(tf, 3), "achieved_tflops": round(tf / (ms * 1e-3), 1),
+            "frac_of_sustained_peak": round(tf / (ms * 1e-3) / sust, 4),
+            "images_per_s_denoise_only": round(n_img * 1000.0 / (DDIM_STEPS * ms), 4),
+            "launches_per_step": int(getattr(eng, "launches_per_step", 0) or 0),
+            "outputs_finite": bool(torch.isfinite(eng.latents()).all().item())}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -163,14 +216,22 @@ def run_ours(args, rank, world, local_rank):
     eng = DenoiseEngine(cfg, usd, csds, dev)
     del usd, csds
     torch.cuda.empty_cache()
-    x, ctx, hints = make_inputs(cfg, 2, 64, 77, 11 + rank)
+    n_img = max(1, args.images_per_gpu)          # images per GPU; the network batch is 2 * n_img (CFG)
+    x, ctx, hints = make_inputs(cfg, 2 * n_img, 64, 77, 11 + rank)
     ts, a, ap = ddim_schedule(DDIM_STEPS)
+
+    def run_steps(k):
+        """k fused steps: ONE graph launch each; the per-step scalars (DDIM coefficients, time-embedding rows) are
+        rows of device tables indexed by a device counter (DenoiseEngine.set_schedule).  Past the 50th step the
+        counter stays on the last row - the same kernels on the same shapes."""
+        for _ in range(k):
+            eng.step()
 
     # ---- device-resident timed region: exactly K denoising steps --------------------------------
     eng.prepare(ctx, hints, [0.5, 1.0])
-    eng.begin(x[:1], guidance=9.0, use_graph=not args.no_graph)
-    for i in range(args.warmup):
-        eng.step(int(ts[i % DDIM_STEPS]), float(a[i % DDIM_STEPS]), float(ap[i % DDIM_STEPS]))
+    eng.set_schedule(ts, a, ap)
+    eng.begin(x[:n_img], guidance=9.0, use_graph=not args.no_graph)
+    run_steps(args.warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -182,9 +243,7 @@ def run_ours(args, rank, world, local_rank):
     if args.profiler_range:
         torch.cuda.profiler.start()          # ncu --profile-from-start off: capture the timed region only
     e0.record()
-    for i in range(args.steps):
-        j = (args.warmup + i) % DDIM_STEPS
-        eng.step(int(ts[j]), float(a[j]), float(ap[j]))
+    run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
     if args.profiler_range:
@@ -235,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
         vsd.update(make_vae_state_dict(SD_VAE, 402, device=dev))
         vae = VaeEngine(SD_VAE, vsd, dev)
         del vsd
-        lat = eng.latents().float()
+        lat = eng.latents().float()[:1]
         src = torch.rand(1, 3, 512, 512, device=dev) * 2 - 1          # the masked source image (prepare_masked_image_latents)
 
         def _time(fn):
@@ -252,8 +311,10 @@ def run_ours(args, rank, world, local_rank):
         vae_ms = _time(lambda: vae.decode_latents(lat))
         vae_enc_ms = _time(lambda: vae.encode(src))
 
-    img_ms = DDIM_STEPS * ms_step + (sam_ms or 0.0) + (vae_ms or 0.0) + (vae_enc_ms or 0.0)
-    value = world * 1000.0 / img_ms
+    # n_img images per GPU share the 50 steps; SAM encode, VAE encode and decode run once per image
+    img_ms = DDIM_STEPS * ms_step + n_img * ((sam_ms or 0.0) + (vae_ms or 0.0) + (vae_enc_ms or 0.0))
+    value = world * n_img * 1000.0 / img_ms
+    step_tflop = STEP_TFLOP * n_img
 
     # ---- roofline of the dominant kernel (ea_gemm_kernel), live CUDA events ----------------------
     probe = GemmProbe(ops)
@@ -276,7 +337,10 @@ def run_ours(args, rank, world, local_rank):
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     # operand bytes the algorithm needs per launch (A + W + out (+ residual)), averaged over the step's launches
     alg_bytes = 0
-    for a_, w_, out_, kw_, _ in probe.records:
+    flat = []
+    for rec in probe.records:
+        flat += [(a_, w_, o_, k_, 0) for a_, w_, o_, k_ in rec[1]] if rec[0] == "grouped" else [rec]
+    for a_, w_, out_, kw_, _ in flat:
         conv = kw_.get("conv")
         Mrows = conv[0] * conv[1] * conv[2] if conv else (kw_.get("M") or a_.shape[0])
         Kin = conv[3] if conv else w_.shape[1]
@@ -290,63 +354,72 @@ def run_ours(args, rank, world, local_rank):
                 "launches": n_gemm, "gemm_ms_per_step": round(g_ms, 3),
                 "timing": "all ea_gemm launches of one step re-issued back to back in one CUDA graph, CUDA events",
                 "gemm_tflop_per_step": round(g_fl / 1e12, 3),
-                "whole_step": {"tflop": STEP_TFLOP, "achieved": round(STEP_TFLOP / (ms_step * 1e-3), 1),
-                               "frac": round(STEP_TFLOP / (ms_step * 1e-3) / sust, 4)}}
+                "whole_step": {"tflop": step_tflop, "achieved": round(step_tflop / (ms_step * 1e-3), 1),
+                               "frac": round(step_tflop / (ms_step * 1e-3) / sust, 4)}}
 
     # ---- e2e: host buffers in, host result out, through the public engine API ---------------------
     e2e = None
     if (rank == 0 or world > 1) and not args.no_e2e:
-        # One image end to end through the public engine API, inputs in PINNED HOST memory:
+        # n_img images per GPU end to end through the public engine API, inputs in PINNED HOST memory:
         #   H2D preprocessed image -> SAM ViT-H encode -> D2H embedding (what the mask decoder / AMG consume)
         #   H2D prompt embeddings, ControlNet conditioning images, initial noise -> prepare (ctx K/V, hint
-        #   stacks) -> 50 fused steps -> D2H latents.
-        # One untimed warm-up image (CUDA-graph capture, allocator), then n_img timed images.
-        hx, hctx = x[:1].pin_memory(), ctx.pin_memory()
+        #   stacks) -> 50 fused steps (one graph launch each) -> VAE decode -> uint8 image tiles [n, H, W, 3]
+        #   -> (world > 1) ONE NCCL all-gather of every rank's tiles -> D2H.
+        # One untimed warm-up pass (CUDA-graph capture, allocator), then n_rep timed passes.
+        hx, hctx = x[:n_img].pin_memory(), ctx.pin_memory()
         hh = [h.pin_memory() for h in hints]
         himg = torch.randn(1, 3, 1024, 1024).pin_memory() if sam is not None else None
         hsrc = (torch.rand(1, 3, 512, 512) * 2 - 1).pin_memory() if vae is not None else None
-        n_img = 3
+        n_rep = 3
+        from editanything_b200.sharding import gather_sharded
 
-        def one_image():
+        def one_pass():
             emb = None
-            if sam is not None:
-                emb = sam.encode(himg.to(dev, non_blocking=True)).cpu()
-            if vae is not None:      # masked-image latents (utils/...inpaint.py:1056-1105); consumed by the blend
-                vae.encode(hsrc.to(dev, non_blocking=True)).latent_dist.sample()
+            for _ in range(n_img):
+                if sam is not None:
+                    emb = sam.encode(himg.to(dev, non_blocking=True)).cpu()
+                if vae is not None:  # masked-image latents (utils/...inpaint.py:1056-1105); consumed by the blend
+                    vae.encode(hsrc.to(dev, non_blocking=True)).latent_dist.sample()
             eng.prepare(hctx.to(dev, non_blocking=True), [h.to(dev, non_blocking=True) for h in hh], [0.5, 1.0])
+            eng.set_schedule(ts, a, ap)
             eng.begin(hx.to(dev, non_blocking=True), guidance=9.0, use_graph=not args.no_graph)
-            for i in range(DDIM_STEPS):
-                eng.step(int(ts[i]), float(a[i]), float(ap[i]))
-            if vae is not None:
-                return vae.decode_latents(eng.latents().float()).cpu(), emb      # the decoded [1,3,512,512] image
-            return eng.latents().cpu(), emb
+            for _ in range(DDIM_STEPS):
+                eng.step()
+            if vae is not None:   # decoded images as uint8 tiles (what numpy_to_pil makes of them, :333-335)
+                img = torch.cat([vae.decode_latents(eng.latents()[i:i + 1].float()) for i in range(n_img)])
+                res = (img.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous()
+            else:
+                res = eng.latents()
+            if world > 1:
+                res = gather_sharded(res, world * n_img, rank, world) if n_img == 1 else \
+                    torch.cat(_all_gather_list(res, world))          # the single end-of-job collective
+            return res.cpu(), emb
 
-        one_image()
+        one_pass()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(n_img):
-            res, emb = one_image()
+        for _ in range(n_rep):
+            res, emb = one_pass()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
-            from editanything_b200.sharding import gather_sharded
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
-            allres = gather_sharded(res.to(dev), world, rank, world)   # the single end-of-job collective
-            assert allres.shape[0] == world
-        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh) + (himg.numel() if himg is not None else 0) +
-               (hsrc.numel() if hsrc is not None else 0)) * 4
-        d2h = (res.numel() + (emb.numel() if emb is not None else 0)) * 4
-        e2e = {"value": round(world * n_img / dt, 4), "unit": "images/s",
+            assert res.shape[0] == world * n_img
+        h2d = (hx.numel() + hctx.numel() + sum(h.numel() for h in hh)) * 4 + n_img * (
+            (himg.numel() if himg is not None else 0) + (hsrc.numel() if hsrc is not None else 0)) * 4
+        d2h = res.numel() * res.element_size() + n_img * (emb.numel() * 4 if emb is not None else 0)
+        e2e = {"value": round(world * n_img * n_rep / dt, 4), "unit": "images/s",
                "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": d2h // DDIM_STEPS,
-               "ms_per_image": round(dt / n_img * 1e3, 2), "images_timed": n_img,
-               "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host ctx / hints / "
-                       "noise -> H2D -> prepare (ctx K/V, hint stacks) -> 50 fused steps -> VAE decode -> D2H fp32 image; pinned "
-                       "host source image -> H2D -> VAE encode; 1 untimed warm-up image; text encoder / SAM mask decoder "
-                       "not included (SURVEY.md 8f)"}
+               "ms_per_image": round(dt / (n_rep * n_img) * 1e3, 2), "images_timed": n_rep * n_img,
+               "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host source "
+                       "image -> H2D -> VAE encode; pinned host ctx / hints / noise -> H2D -> prepare (ctx K/V, hint "
+                       "stacks) -> 50 fused steps (one graph launch per step) -> VAE decode -> uint8 tiles -> "
+                       "(N > 1: one NCCL all-gather of all ranks' tiles, inside the timed region) -> D2H; 1 untimed "
+                       "warm-up pass; text encoder / SAM mask decoder not included (SURVEY.md 8f)"}
 
     line = {
         "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
@@ -354,18 +427,32 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16 storage / fp32 accumulate" if ops.half_dtype() == torch.float16 else "bf16 storage / fp32 accumulate",
         "data": "synthetic inputs, seeded random weights (SD1.5 topology, 859.5M + 2x361.3M params)",
-        "config": {"workload": "BASELINE.json configs[1]: SD1.5 ControlNet-inpaint 512x512, 50 DDIM steps, batch=1/GPU "
-                               "(+CFG => B=2), SAM+inpaint ControlNets, L=77",
-                   "global_batch": world, "parallelism": f"dp{world} (one image per GPU, final all-gather)",
+        "config": {"workload": ("BASELINE.json configs[1]: SD1.5 ControlNet-inpaint 512x512, 50 DDIM steps, batch=1/GPU "
+                                "(+CFG => B=2), SAM+inpaint ControlNets, L=77") if n_img == 1 else
+                               (f"BASELINE.json configs[3] shard: SD1.5 ControlNet-inpaint 512x512, 50 DDIM steps, "
+                                f"batch={n_img}/GPU (+CFG => B={2 * n_img}), SAM+inpaint ControlNets, L=77"),
+                   "global_batch": world * n_img,
+                   "parallelism": f"dp{world} ({n_img} image(s) per GPU, final all-gather of uint8 tiles)",
                    "l2": "weights touched per step (3.16 GB) exceed the 126 MB L2; no explicit flush",
                    "cuda_graph": not args.no_graph, "sam_ms_per_image": sam_ms, "sam": sam_note,
                    "vae_decode_ms_per_image": vae_ms, "vae_encode_ms_per_image": vae_enc_ms,
-                   "image": "image_ms = 50 x ms_per_step + SAM encode + VAE encode of the masked source image "
-                            "(512x512 -> 64x64 latents) + VAE decode (64x64 -> 512x512), kl-f8",
+                   "image": "image_ms = 50 x ms_per_step + images_per_gpu x (SAM encode + VAE encode of the masked source "
+                            "image (512x512 -> 64x64 latents) + VAE decode (64x64 -> 512x512), kl-f8); "
+                            "value = n_gpus x images_per_gpu x 1000 / image_ms",
+                   "images_per_gpu": n_img,
                    "image_ms": round(img_ms, 3), "outputs_finite": finite},
         "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roofline, "e2e": e2e,
     }
+    if n_img == 1 and not args.no_batch4:
+        # BASELINE.json configs[3] (4 images per GPU): where the weight-bound 8x8 / 16x16 levels amortise
+        line["config"]["batch4"] = measure_batch_block(eng, cfg, 4, rank, sust, args, ts, a, ap)
+        if world > 1:
+            t = torch.tensor([line["config"]["batch4"]["ms_per_step"]], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            b4 = line["config"]["batch4"]
+            b4["ms_per_step"] = round(t.item(), 4)
+            b4["images_per_s_denoise_only"] = round(world * 4 * 1000.0 / (DDIM_STEPS * t.item()), 4)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_steps=1)
     if rank == 0:
@@ -507,6 +594,9 @@ def main():
                     help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--no-sam", action="store_true", help="profiling runs only: skip the SAM encoder leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only (ncu): skip the e2e leg")
+    ap.add_argument("--images-per-gpu", type=int, default=1,
+                    help="images per GPU (network batch = 2x with CFG); 4 = BASELINE.json configs[3]")
+    ap.add_argument("--no-batch4", action="store_true", help="skip the extra configs[3] (4 images per GPU) block")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -56,6 +56,7 @@ class GnArgs(C.Structure):
         ("B", C.c_int), ("HW", C.c_int), ("C", C.c_int), ("groups", C.c_int),
         ("eps", C.c_float), ("silu", C.c_int), ("two_pass", C.c_int),
         ("workspace", C.c_void_p),
+        ("n_nets", C.c_int), ("gamma_more", C.c_void_p * 2), ("beta_more", C.c_void_p * 2),
     ]
 
 
@@ -70,6 +71,7 @@ SYMBOLS = {
     "ea_reset_launch_count": (None, []),
     "ea_set_pdl": (None, [_I]),
     "ea_gemm": (_I, [C.POINTER(GemmArgs), _P]),
+    "ea_gemm_grouped": (_I, [C.POINTER(GemmArgs), _I, _P]),
     "ea_gemm_plan": (_I, [_I, _I, _I, _I, _L, _I, C.POINTER(C.c_int)]),
     "ea_attention": (_I, [C.POINTER(AttnArgs), _P]),
     "ea_groupnorm": (_I, [C.POINTER(GnArgs), _P]),

@@ -77,6 +77,21 @@ struct GemmKParams {
   int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
+// One launch can run up to GEMM_MAX_GROUPS independent problems of the SAME shape and launch plan (ea_gemm_grouped):
+// the UNet encoder and the ControlNets are the same network with different weights reading the same latent
+// (cldm/cldm.py:22-45,284-305), so every one of their layers is one grouped launch.  Each group has its own tensor
+// maps and parameter block (any pointers), selected by blockIdx.z / splits (tile index / tiles for the persistent
+// kernel); with NG = 1 the selection is a compile-time constant and the code is the ungrouped kernel.
+static constexpr int GEMM_MAX_GROUPS = 3;
+struct GemmGroup {
+  CUtensorMap tmA0, tmA1, tmA2, tmA3, tmAx, tmB;
+  GemmKParams p;
+};
+template <int NG>
+struct GemmLaunch {
+  GemmGroup g[NG];
+};
+
 __device__ __forceinline__ void tile_origin(const GemmKParams& p, int tm, int& n0, int& h0,
                                             int& w0) {
   // tiles enumerate (image block, tile row, tile col); an image block is bn images
@@ -357,12 +372,21 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 // TWO = true: CTA pairs (cluster of 2 along M) run tcgen05.mma.cta_group::2 with M = 256; each CTA
 // stages its own A tile and HALF of the B tile (rows tn*BN + rank*BN/2 ...), the leader issues.
-template <bool TWO>
+template <bool TWO, int NG>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-               const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmB,
-               const GemmKParams p) {
+ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
+  // group of this CTA: blockIdx.z = group * splits + split (every group has the same shape and plan)
+  const int n_split0 = L.g[0].p.splits;
+  const int gi = NG == 1 ? 0 : (int)blockIdx.z / n_split0;
+  const int zsplit = NG == 1 ? (int)blockIdx.z : (int)blockIdx.z - gi * n_split0;
+  const GemmGroup& GG = L.g[gi];
+  const GemmKParams& p = GG.p;
+  const CUtensorMap& tmA0 = GG.tmA0;
+  const CUtensorMap& tmA1 = GG.tmA1;
+  const CUtensorMap& tmA2 = GG.tmA2;
+  const CUtensorMap& tmA3 = GG.tmA3;
+  const CUtensorMap& tmAx = GG.tmAx;
+  const CUtensorMap& tmB = GG.tmB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages] x (A 16 KB | B BN*128 B), then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -385,7 +409,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int tm = blockIdx.x;
   const int tn = blockIdx.y;
 #ifdef EA_GEMM_TIMING
-  const bool dbg_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool dbg_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && gi == 0;
   if (threadIdx.x == 0) {
     EA_GT1(0);
     EA_CH(0);
@@ -393,7 +417,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 #endif
   const int nkb_total = p.nkb_main + p.nkb_extra;
-  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb0 = zsplit * p.kb_per_split;
   const int kb1 = min(nkb_total, kb0 + p.kb_per_split);
 
   if (warp == W_TMA && lane == 0) {
@@ -754,7 +778,7 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       //      split CTA reduces and finishes a 1/splits share of the tile's (row, 32-col) units.
       const int tile_id = tn * gridDim.x + tm;
       float* wtile = p.ws + (size_t)tile_id * p.splits * (BM * p.BN);
-      float* mine = wtile + (size_t)blockIdx.z * (BM * p.BN);
+      float* mine = wtile + (size_t)zsplit * (BM * p.BN);
       for (int c = 0; c < p.BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
@@ -789,8 +813,8 @@ ea_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (!p.no_spin || take_all) {
       const int chunks = geglu ? (half_bn >> 5) : (p.BN >> 5);
       const int units = BM * chunks;
-      const int u0 = take_all ? 0 : (int)(((long long)units * blockIdx.z) / p.splits);
-      const int u1 = take_all ? units : (int)(((long long)units * (blockIdx.z + 1)) / p.splits);
+      const int u0 = take_all ? 0 : (int)(((long long)units * zsplit) / p.splits);
+      const int u1 = take_all ? units : (int)(((long long)units * (zsplit + 1)) / p.splits);
       // Stage 1 (all 128 threads, float4 granularity, loads of the sibling partials unrolled for
       // memory-level parallelism) sums this CTA's share into the now-idle pipeline smem; stage 2
       // runs the fused epilogue on whole 32-column units.  Pieces of <= 128 units (<= 35 KB, the pipeline
@@ -939,12 +963,20 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // second warp-group takes every other 64-column group of the accumulator.  The one-warp-per-sub-partition
 // epilogue is instruction-latency bound (3-5 us per tile, profiles/r01p_exp_step_chain_gemm_in_context.txt);
 // a second warp on the same scheduler hides it, also for grids of a single wave.
-template <int EPI_WG>
+template <int EPI_WG, int NG>
 __global__ void __launch_bounds__(64 + 128 * EPI_WG, 1)
-ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                          const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmB,
-                          const GemmKParams p, const int num_tiles, const int m_tiles) {
+ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int tiles_per_group, const int m_tiles,
+                          const int n_groups) {
+  // the tile list runs over (group, tile): every group has the same shape and plan; `p` below = the shared fields
+  // (group 0), each tile re-binds `p` / the tensor maps to its own group
+  const GemmKParams& p = L.g[0].p;
+  const int num_tiles = tiles_per_group * (NG == 1 ? 1 : n_groups);
+#define EA_PERSIST_TILE_GROUP()                                                    \
+  const int gi = NG == 1 ? 0 : tile / tiles_per_group;                             \
+  const int gtile = NG == 1 ? tile : tile - gi * tiles_per_group;                  \
+  const GemmGroup& GG = L.g[gi];                                                   \
+  const GemmKParams& p = GG.p;                                                     \
+  const int tm = gtile % m_tiles, tn = gtile / m_tiles;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -971,14 +1003,15 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
   const uint32_t acc_cols = tmem_cols_for(p.BN);
 
   if (warp == PW_TMA && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB);
+    const int g0 = NG == 1 ? 0 : ((int)blockIdx.x / tiles_per_group) % NG;
+    tma_prefetch_desc(&L.g[g0].tmA0);
+    tma_prefetch_desc(&L.g[g0].tmB);
     if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmA2);
-      tma_prefetch_desc(&tmA3);
+      tma_prefetch_desc(&L.g[g0].tmA1);
+      tma_prefetch_desc(&L.g[g0].tmA2);
+      tma_prefetch_desc(&L.g[g0].tmA3);
     }
-    if (p.nkb_extra > 0) tma_prefetch_desc(&tmAx);
+    if (p.nkb_extra > 0) tma_prefetch_desc(&L.g[g0].tmAx);
   }
   if (warp == PW_TMA && lane == 1) {
     for (int s = 0; s < p.stages; ++s) {
@@ -1006,7 +1039,13 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
       uint8_t* sa = smem;
       const int cin = p.cin_blocks * BK;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % m_tiles, tn = tile / m_tiles;
+        EA_PERSIST_TILE_GROUP()
+        const CUtensorMap& tmA0 = GG.tmA0;
+        const CUtensorMap& tmA1 = GG.tmA1;
+        const CUtensorMap& tmA2 = GG.tmA2;
+        const CUtensorMap& tmA3 = GG.tmA3;
+        const CUtensorMap& tmAx = GG.tmAx;
+        const CUtensorMap& tmB = GG.tmB;
         const int bcol = tn * p.BN;
         if (p.mode == EA_GEMM_LINEAR) {
           const int arow = tm * BM;
@@ -1094,14 +1133,14 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     const int et = threadIdx.x;          // 0 .. EPI_THREADS-1
     const bool geglu = p.act == EA_ACT_GEGLU;
     const int half_bn = p.BN >> 1;
-    const bool has_res = p.residual != nullptr;
     uint4* stg = reinterpret_cast<uint4*>(stg_base + warp * 4096);
     uint4* stg2 = reinterpret_cast<uint4*>(stg_base + 4096 * EPI_WARPS + warp * 4096);
     constexpr int GSTEP = 64 * EPI_WG;   // column distance between two groups of one warp-group
     int abuf = 0, it = 0;
     uint32_t fphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile % m_tiles, tn = tile / m_tiles;
+      EA_PERSIST_TILE_GROUP()
+      const bool has_res = p.residual != nullptr;
       const RowInfo ri = row_info(p, tm, r);
       const int ncol0 = tn * p.BN;
       float* cbt = cb + (it & 1) * 512;
@@ -1282,6 +1321,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     tc_fence_after();
     tmem_dealloc(tmem_base, 2u * acc_cols);
   }
+#undef EA_PERSIST_TILE_GROUP
 }
 
 // ---- launch planner -------------------------------------------------------------------
@@ -1308,8 +1348,10 @@ static const double PL_SPLIT_COL = pl_env("EA_PL_SPLIT_COL", 8.0);
 static const double PL_SPLIT_FIX = pl_env("EA_PL_SPLIT_FIX", 7000.0);
 static constexpr double PL_START = 3800.0, PL_START_TWO = 2100.0, PL_EPI = 50.0, PL_EPI_RES = 21.0;
 
+// groups: identical problems run by the same launch - they multiply the CTAs (waves, what is left to split K
+// over) but not the reuse of one weight tile across its M-tiles.
 static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, int n_sm,
-                          bool allow_two, bool has_res = false) {
+                          bool allow_two, bool has_res = false, int groups = 1) {
   const double epi_col = (PL_EPI + (has_res ? PL_EPI_RES : 0.0)) * (act == EA_ACT_GEGLU ? 0.84 : 1.0);
   // measured on B200 (profiles/r01c): one SM fills shared memory at ~45 B/clk whatever the tile
   // shape (cuBLAS sits at the same cap with 2-CTA 256x256 tiles), the chip at ~6000 B/clk from L2
@@ -1323,7 +1365,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
       if (N <= BN - 32) continue;
       const int nt = (N + BN - 1) / BN;
       const int mt2 = (mt + 1) / 2 * 2;
-      const long long ctas = (long long)mt2 * nt;
+      const long long ctas = (long long)mt2 * nt * groups;
       const int stage_bytes = BM * BK * 2 + (BN / 2) * BK * 2;
       const int tmem = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
       for (int occ = 2; occ >= 1; --occ) {
@@ -1356,7 +1398,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
     if (act == EA_ACT_GEGLU && BN != 128) continue;  // weights are interleaved per 128-row block
     if (BN > 32 && N <= BN - 32) continue;            // a narrower tile covers N just as well
     const int nt = (N + BN - 1) / BN;
-    const long long tiles = (long long)mt * nt;
+    const long long tiles = (long long)mt * nt * groups;
     const int stage_bytes = BM * BK * 2 + BN * BK * 2;
     const int tmem = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     for (int occ = 2; occ >= 1; --occ) {
@@ -1409,7 +1451,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
   }
   // Measured deviations from the cost model (profiles/r01r_exp_splitk_sweep.txt, B200, 148 SMs): two shapes of the
   // 16x16 level where a sweep over (BN, splits) beat the model's pick by 13-14 %.
-  if (ws_floats > 0 && mt == 4 && N == 1280 && act != EA_ACT_GEGLU) {
+  if (ws_floats > 0 && groups == 1 && mt == 4 && N == 1280 && act != EA_ACT_GEGLU) {
     if (nkb == 80 && best.splits > 1)                       // ff2: 512 x 1280, K = 5120: 24.1 vs 28.0 us
       best = {64, 8, 1, nkb, 1, best.cost, 0};
     else if (nkb >= 360 && nkb <= 400 && best.BN == 256 &&  // conv 2560 -> 1280 (+ 1x1 skip): 45.5 vs 52.5 us
@@ -1466,14 +1508,19 @@ extern "C" int ea_gemm_plan(int m_tiles, int N, int k_blocks, int act, long long
   return pl.BN ? EA_OK : EA_ERR_SHAPE;
 }
 
-extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// Everything of one problem that does not depend on the launch plan: validation, the parameter block, the A maps.
+struct GemmShape {
+  int m_tiles, nkb;
+  long long Ktot;
+  bool ln_any;
+};
+
+static int gemm_fill_group(const ea_gemm_args* a, GemmGroup& G, GemmShape& sh) {
   if (!a || !a->a || !a->w || (!a->out && !a->out_f32)) return EA_ERR_ARG;
   if (a->mode < 0 || a->mode > EA_GEMM_CONV_S2A) return EA_ERR_ARG;
   if (a->N <= 0 || a->M <= 0) return EA_ERR_ARG;
   if (a->N % 8 != 0) return EA_ERR_SHAPE;
-
-  GemmKParams p;
+  GemmKParams& p = G.p;
   memset(&p, 0, sizeof(p));
 #ifdef EA_GEMM_TIMING
   p.dbg_id = g_dbg_launch++;
@@ -1495,8 +1542,8 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   p.act = a->act;
   p.out_scale = a->out_scale;
   p.accumulate = a->accumulate;
-  const bool ln_any = a->rowstats_out || a->ln_stats;
-  if (ln_any) {
+  sh.ln_any = a->rowstats_out || a->ln_stats;
+  if (sh.ln_any) {
     if (a->mode != EA_GEMM_LINEAR || a->rowvec || a->out_f32 || a->accumulate) return EA_ERR_ARG;
     if (a->rowstats_out && (a->N % 32 != 0 || a->act == EA_ACT_GEGLU)) return EA_ERR_SHAPE;
     if (a->ln_stats && (!a->ln_g || a->ln_parts <= 0 || a->K != a->ln_parts * 32)) return EA_ERR_ARG;
@@ -1510,22 +1557,18 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   if (p.ldo % 8 != 0 || (p.residual && p.ldr % 8 != 0) || (p.out2 && p.ldo2 % 8 != 0))
     return EA_ERR_SHAPE;
 
-  CUtensorMap tmA[4], tmAx, tmB;
-  memset(tmA, 0, sizeof(tmA));
-  memset(&tmAx, 0, sizeof(tmAx));
-  int m_tiles;
-  long long Ktot;
+  CUtensorMap* tmA[4] = {&G.tmA0, &G.tmA1, &G.tmA2, &G.tmA3};
   if (a->mode == EA_GEMM_LINEAR) {
     if (a->K % 8 != 0 || a->lda % 8 != 0) return EA_ERR_SHAPE;
     p.nkb_main = (a->K + BK - 1) / BK;
     p.nkb_extra = 0;
     p.cin_blocks = 1;
-    m_tiles = (a->M + BM - 1) / BM;
-    Ktot = a->K;
-    if (encode_2d(&tmA[0], a->a, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM))
+    sh.m_tiles = (a->M + BM - 1) / BM;
+    sh.Ktot = a->K;
+    if (encode_2d(tmA[0], a->a, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, BK, BM))
       return EA_ERR_TMAP;
-    tmA[1] = tmA[2] = tmA[3] = tmA[0];
-    tmAx = tmA[0];
+    G.tmA1 = G.tmA2 = G.tmA3 = G.tmA0;
+    G.tmAx = G.tmA0;
   } else {
     const int H = a->H, W = a->W, B = a->Bsz, C = a->Cin;
     if (C % 64 != 0 || H <= 0 || W <= 0 || B <= 0) return EA_ERR_SHAPE;
@@ -1537,15 +1580,15 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
     p.cin_blocks = C / 64;
     p.nkb_main = 9 * p.cin_blocks;
     p.nkb_extra = 0;
-    m_tiles = ((B + p.bn - 1) / p.bn) * p.tiles_w * p.tiles_h;
-    Ktot = 9LL * C;
+    sh.m_tiles = ((B + p.bn - 1) / p.bn) * p.tiles_w * p.tiles_h;
+    sh.Ktot = 9LL * C;
     const long long lda = a->lda > 0 ? a->lda : C;  // channel stride of one pixel (elements)
     uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     if (a->mode == EA_GEMM_CONV_S1) {
       uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       uint64_t st[3] = {(uint64_t)lda * 2, (uint64_t)lda * W * 2, (uint64_t)lda * W * H * 2};
-      if (encode_4d(&tmA[0], a->a, dims, st, box)) return EA_ERR_TMAP;
-      tmA[1] = tmA[2] = tmA[3] = tmA[0];
+      if (encode_4d(tmA[0], a->a, dims, st, box)) return EA_ERR_TMAP;
+      G.tmA1 = G.tmA2 = G.tmA3 = G.tmA0;
     } else {
       // input is (2H x 2W); four phase views (ph, pw) each of H x W
       const int Hin = 2 * H, Win = 2 * W;
@@ -1556,45 +1599,84 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
           uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
           uint64_t st[3] = {(uint64_t)lda * 2 * 2, (uint64_t)lda * Win * 2 * 2,
                             (uint64_t)lda * Win * Hin * 2};
-          if (encode_4d(&tmA[ph * 2 + pw], base, dims, st, box)) return EA_ERR_TMAP;
+          if (encode_4d(tmA[ph * 2 + pw], base, dims, st, box)) return EA_ERR_TMAP;
         }
     }
-    tmAx = tmA[0];
+    G.tmAx = G.tmA0;
     if (a->a_extra) {
       if (a->mode != EA_GEMM_CONV_S1 || a->Cin_extra % 64 != 0) return EA_ERR_SHAPE;
       const long long ldx = a->ld_extra > 0 ? a->ld_extra : a->Cin_extra;
       uint64_t dims[4] = {(uint64_t)a->Cin_extra, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       uint64_t st[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * W * 2, (uint64_t)ldx * W * H * 2};
-      if (encode_4d(&tmAx, a->a_extra, dims, st, box)) return EA_ERR_TMAP;
+      if (encode_4d(&G.tmAx, a->a_extra, dims, st, box)) return EA_ERR_TMAP;
       p.nkb_extra = a->Cin_extra / 64;
-      Ktot += a->Cin_extra;
+      sh.Ktot += a->Cin_extra;
     }
   }
-  const int nkb = p.nkb_main + p.nkb_extra;
+  sh.nkb = p.nkb_main + p.nkb_extra;
+  return EA_OK;
+}
+
+// groups of one launch must be the same problem with different pointers
+static bool gemm_same_problem(const ea_gemm_args* a, const ea_gemm_args* b) {
+  return a->mode == b->mode && a->M == b->M && a->N == b->N && a->K == b->K && a->Bsz == b->Bsz && a->H == b->H &&
+         a->W == b->W && a->Cin == b->Cin && a->Cin_extra == b->Cin_extra && (!a->a_extra) == (!b->a_extra) &&
+         a->act == b->act && a->accumulate == b->accumulate && (!a->out_f32) == (!b->out_f32) &&
+         (!a->rowvec) == (!b->rowvec) && a->rows_per_batch == b->rows_per_batch &&
+         (!a->rowstats_out) == (!b->rowstats_out) && (!a->ln_stats) == (!b->ln_stats) && a->ln_parts == b->ln_parts &&
+         a->force_bn == b->force_bn && a->force_stages == b->force_stages && a->force_splits == b->force_splits &&
+         a->force_2cta == b->force_2cta && a->no_spin == b->no_spin && a->force_persistent == b->force_persistent;
+}
+
+template <typename K>
+static int set_max_smem(K kernel, int bytes, int& cached) {
+  if (bytes > cached) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return EA_ERR_CUDA;
+    cached = bytes;
+  }
+  return EA_OK;
+}
+
+extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!args || n_groups < 1 || n_groups > GEMM_MAX_GROUPS) return EA_ERR_ARG;
+  const ea_gemm_args* a = &args[0];          // shape, flags and plan come from group 0
+  static GemmLaunch<GEMM_MAX_GROUPS> L;      // host-side staging (ea_gemm is not re-entrant per process, see header)
+  GemmShape sh0;
+  memset(&L, 0, sizeof(L));
+  for (int g = 0; g < n_groups; ++g) {
+    GemmShape shg;
+    if (g > 0 && !gemm_same_problem(a, &args[g])) return EA_ERR_ARG;
+    const int rc = gemm_fill_group(&args[g], L.g[g], g == 0 ? sh0 : shg);
+    if (rc != EA_OK) return rc;
+  }
+  const int m_tiles = sh0.m_tiles, nkb = sh0.nkb;
+  const bool ln_any = sh0.ln_any;
+  const GemmKParams& p0 = L.g[0].p;
+  const int G = n_groups;
   // workspace: [0, 64 KB) arrival counters (int, zero between launches), then fp32 partial tiles
   const long long ws_floats =      // the LayerNorm fold lives in the unsplit epilogues only
       (a->workspace && a->workspace_bytes > 65536 && !ln_any) ? (a->workspace_bytes - 65536) / 4 : 0;
   static const int two_env = [] { const char* e = getenv("EA_GEMM_2CTA"); return e ? atoi(e) : -1; }();
   const bool can_two = a->mode != EA_GEMM_CONV_S2 && a->mode != EA_GEMM_CONV_S2A && two_env != 0 && a->force_2cta >= 0;
-  // Persistent variant (experimental): wanted when forced, or with EA_GEMM_PERSIST=1 for multi-wave grids.
   // EA_GEMM_PERSIST: unset / 3 = per-launch choice (below), 0 = never, 1 / 2 = wherever the launch qualifies
   // (4 / 8 epilogue warps; the A/B switches of profiles/r02a_gemm_breakdown_*).
   static const int persist_env = [] { const char* e = getenv("EA_GEMM_PERSIST"); return e ? atoi(e) : 3; }();
   const bool batch_ok =
       !a->rowvec || (a->mode == EA_GEMM_LINEAR
                          ? (a->rows_per_batch == 0 || a->rows_per_batch >= BM || a->rows_per_batch == BM / 2)
-                         : p.bn <= 2);      // a tile may span at most two batch elements (fast epilogue)
+                         : p0.bn <= 2);      // a tile may span at most two batch elements (fast epilogue)
   const bool persist_ok = !a->out_f32 && !a->accumulate && a->force_splits <= 1 && a->force_2cta <= 0 &&
                           (a->act == EA_ACT_GEGLU || batch_ok);
   bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
   const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env >= 2)) ? 2 : 1;
-  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, a->residual != nullptr);
+  const bool has_res = a->residual != nullptr;
+  GemmPlan plan = plan_gemm(m_tiles, a->N, nkb, a->act, ws_floats, sm_count(), can_two, has_res, G);
   if (persist && a->force_persistent == 0) {
-    // auto mode (environment switch): never where the planner splits K (weight-streaming small-M layers; first
-    // A/B on hardware: the unsplit 8x8 convolutions took 50 us instead of 20), and the 4-epilogue-warp variant only
-    // for grids of more than one wave (its gain is the overlap across tiles; the 8-warp variant also speeds up
-    // the epilogue of a single tile)
-    const long long tiles0 = (long long)m_tiles * ((a->N + plan.BN - 1) / plan.BN);
+    // auto mode: never where the planner splits K (weight-streaming small-M layers; first A/B on hardware: the
+    // unsplit 8x8 convolutions took 50 us instead of 20), and the 4-epilogue-warp variant only for grids of more
+    // than one wave (its gain is the overlap across tiles; the 8-warp variant also speeds up a single tile)
+    const long long tiles0 = (long long)G * m_tiles * ((a->N + plan.BN - 1) / plan.BN);
     if (plan.splits > 1 || (persist_wg == 1 && tiles0 <= sm_count())) persist = false;
     if (persist && persist_env == 3) {
       // Default: the 8-epilogue-warp persistent kernel wherever its tile list balances over the SMs - at most one
@@ -1602,13 +1684,13 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
       // wins 7-27 % on the GEGLU projections, the C x C linears of the 32x32 / 16x16 levels and the long-K
       // convolutions (sum over a step's 362 launches 6.16 -> 5.86 ms), and loses 6-20 % where 148 < tiles < 296
       // leaves half the SMs a second tile to do alone (64 x 4 tiles: 8192 x 320 x 320, 8192 x 640 x 5760).
-      const GemmPlan pp = plan.two ? plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, a->residual != nullptr) : plan;
-      const long long tiles_p = (long long)m_tiles * ((a->N + pp.BN - 1) / pp.BN);
+      const GemmPlan pp = plan.two ? plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, has_res, G) : plan;
+      const long long tiles_p = (long long)G * m_tiles * ((a->N + pp.BN - 1) / pp.BN);
       if (tiles_p > sm_count() && tiles_p < 2LL * sm_count()) persist = false;
     }
   }
   if (persist && (plan.two || plan.splits > 1))   // the persistent kernel has no CTA pairs and no split-K
-    plan = plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, a->residual != nullptr);
+    plan = plan_gemm(m_tiles, a->N, nkb, a->act, 0, sm_count(), false, has_res, G);
   if (a->force_2cta > 0 && can_two && !plan.two) {  // testing: pair mode with the 1-CTA tile width
     plan.two = 1; plan.splits = 1; plan.kbps = nkb;
     if (plan.BN < 64) plan.BN = 64;
@@ -1631,94 +1713,122 @@ extern "C" int ea_gemm(const ea_gemm_args* a, void* stream_) {
   }
   if (ln_any && plan.splits > 1) return EA_ERR_ARG;
   const int two = plan.two && plan.splits == 1 && plan.BN >= 64 && plan.BN % 32 == 0;
-  p.BN = plan.BN;
-  if (p.BN < 32 || p.BN > 256 || p.BN % 32 != 0) return EA_ERR_ARG;
-  if (a->act == EA_ACT_GEGLU && (a->N % 128 != 0 || p.BN != 128)) return EA_ERR_SHAPE;
-  const int n_tiles = (a->N + p.BN - 1) / p.BN;
-  p.splits = plan.splits;
-  p.kb_per_split = plan.kbps;
-  p.no_spin = a->no_spin;
-  if (p.splits > 1) {
-    const long long tiles = (long long)m_tiles * n_tiles;
-    if (!ws_floats || tiles > 8192 || tiles * p.splits * (long long)(BM * p.BN) > ws_floats)
-      return EA_ERR_SHAPE;
-    p.cnt = reinterpret_cast<int*>(a->workspace);
-    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + 65536);
-  }
-  const long long ldw = a->ldw > 0 ? a->ldw : Ktot;
-  if (ldw % 8 != 0) return EA_ERR_SHAPE;
-  if (encode_2d(&tmB, a->w, (uint64_t)Ktot, (uint64_t)a->N, (uint64_t)ldw * 2, BK,
-                (uint32_t)(two ? p.BN / 2 : p.BN)))
-    return EA_ERR_TMAP;
+  const int BN = plan.BN;
+  if (BN < 32 || BN > 256 || BN % 32 != 0) return EA_ERR_ARG;
+  if (a->act == EA_ACT_GEGLU && (a->N % 128 != 0 || BN != 128)) return EA_ERR_SHAPE;
+  const int n_tiles = (a->N + BN - 1) / BN;
+  const long long tiles = (long long)m_tiles * n_tiles;      // per group
+  if (plan.splits > 1 &&
+      (!ws_floats || tiles * G > 8192 || tiles * G * plan.splits * (long long)(BM * BN) > ws_floats))
+    return EA_ERR_SHAPE;
 
-  if (persist && !two && p.splits == 1) {
-    const int sbp = BM * BK * 2 + p.BN * BK * 2;
+  // plan-dependent part of every group: tile shape, split-K scratch, the B map
+  const bool persist_launch = persist && !two && plan.splits == 1;
+  int stages = 0, smem_bytes = 0, pair_release = 0;
+  if (persist_launch) {
+    const int sbp = BM * BK * 2 + BN * BK * 2;
     const int fixed = 32768 * persist_wg + (2 * 8 + 4) * 8 + 32 + 2 * 2 * 256 * 4 + 1024;   // staging, barriers, slot, bias, align
-    int st = (224 * 1024 - fixed) / sbp;
-    if (st > 8) st = 8;
-    if (a->force_stages > 0 && a->force_stages < st) st = a->force_stages;
-    if (st >= 2) {
-      p.stages = st;
-      p.pair_release = 0;
-      const int smem_p = st * sbp + fixed;
-      static int max_set_p[3] = {0, 0, 0};
-      if (smem_p > max_set_p[persist_wg]) {
-        const cudaError_t se =
-            persist_wg == 2 ? cudaFuncSetAttribute(ea_gemm_persistent_kernel<2>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p)
-                            : cudaFuncSetAttribute(ea_gemm_persistent_kernel<1>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
-        if (se != cudaSuccess) return EA_ERR_CUDA;
-        max_set_p[persist_wg] = smem_p;
-      }
-      const int num_tiles = m_tiles * n_tiles;
-      const int grid_p = num_tiles < sm_count() ? num_tiles : sm_count();
-      const cudaError_t lp =
-          persist_wg == 2 ? ea_launch(ea_gemm_persistent_kernel<2>, dim3((unsigned)grid_p), dim3(64 + 128 * 2),
-                                      (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p,
-                                      num_tiles, m_tiles)
-                          : ea_launch(ea_gemm_persistent_kernel<1>, dim3((unsigned)grid_p), dim3(64 + 128),
-                                      (size_t)smem_p, stream, tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p,
-                                      num_tiles, m_tiles);
-      ea_count_launch();
-      return (lp == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
-    }
+    stages = (224 * 1024 - fixed) / sbp;
+    if (stages > 8) stages = 8;
+    if (a->force_stages > 0 && a->force_stages < stages) stages = a->force_stages;
+    smem_bytes = stages * sbp + fixed;
   }
-  const int stage_bytes = BM * BK * 2 + (two ? p.BN / 2 : p.BN) * BK * 2;
-  int stages = plan.stages;
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  if (stages >= 5 && (stages & 1) && a->force_stages == 0) --stages;   // even: stages are released in pairs
-  p.stages = stages;
-  p.pair_release = (stages >= 4 && stages % 2 == 0) ? 1 : 0;
-  const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * 256 * 4 + 1024;
-  if (p.splits > 1 && !p.no_spin) {
+  const bool use_persist = persist_launch && stages >= 2;
+  if (!use_persist) {
+    const int stage_bytes = BM * BK * 2 + (two ? BN / 2 : BN) * BK * 2;
+    stages = plan.stages;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    if (stages >= 5 && (stages & 1) && a->force_stages == 0) --stages;   // even: stages are released in pairs
+    pair_release = (stages >= 4 && stages % 2 == 0) ? 1 : 0;
+    smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * 256 * 4 + 1024;
+  }
+  for (int g = 0; g < G; ++g) {
+    GemmKParams& p = L.g[g].p;
+    const ea_gemm_args* ag = &args[g];
+    p.BN = BN;
+    p.stages = stages;
+    p.pair_release = pair_release;
+    p.splits = plan.splits;
+    p.kb_per_split = plan.kbps;
+    p.no_spin = a->no_spin;
+    if (p.splits > 1) {   // every group has its own counters and partial tiles in the (shared) workspace
+      p.cnt = reinterpret_cast<int*>(a->workspace) + 2 * g * tiles;
+      p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->workspace) + 65536) +
+             (size_t)g * tiles * p.splits * (BM * BN);
+    }
+    const long long ldw = ag->ldw > 0 ? ag->ldw : sh0.Ktot;
+    if (ldw % 8 != 0) return EA_ERR_SHAPE;
+    if (encode_2d(&L.g[g].tmB, ag->w, (uint64_t)sh0.Ktot, (uint64_t)ag->N, (uint64_t)ldw * 2, BK,
+                  (uint32_t)(two ? BN / 2 : BN)))
+      return EA_ERR_TMAP;
+  }
+  GemmLaunch<1> L1;
+  if (G == 1) L1.g[0] = L.g[0];
+
+  if (use_persist) {
+    static int cache_p[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    const long long total = tiles * G;
+    const int grid_p = (int)(total < sm_count() ? total : sm_count());
+    cudaError_t lp;
+    int rc;
+    if (persist_wg == 2) {
+      if (G == 1) {
+        if ((rc = set_max_smem(ea_gemm_persistent_kernel<2, 1>, smem_bytes, cache_p[2][0]))) return rc;
+        lp = ea_launch(ea_gemm_persistent_kernel<2, 1>, dim3((unsigned)grid_p), dim3(64 + 128 * 2), (size_t)smem_bytes,
+                       stream, L1, (int)tiles, m_tiles, G);
+      } else {
+        if ((rc = set_max_smem(ea_gemm_persistent_kernel<2, GEMM_MAX_GROUPS>, smem_bytes, cache_p[2][1]))) return rc;
+        lp = ea_launch(ea_gemm_persistent_kernel<2, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(64 + 128 * 2),
+                       (size_t)smem_bytes, stream, L, (int)tiles, m_tiles, G);
+      }
+    } else {
+      if (G == 1) {
+        if ((rc = set_max_smem(ea_gemm_persistent_kernel<1, 1>, smem_bytes, cache_p[1][0]))) return rc;
+        lp = ea_launch(ea_gemm_persistent_kernel<1, 1>, dim3((unsigned)grid_p), dim3(64 + 128), (size_t)smem_bytes,
+                       stream, L1, (int)tiles, m_tiles, G);
+      } else {
+        if ((rc = set_max_smem(ea_gemm_persistent_kernel<1, GEMM_MAX_GROUPS>, smem_bytes, cache_p[1][1]))) return rc;
+        lp = ea_launch(ea_gemm_persistent_kernel<1, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(64 + 128),
+                       (size_t)smem_bytes, stream, L, (int)tiles, m_tiles, G);
+      }
+    }
+    ea_count_launch();
+    return (lp == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
+  }
+  if (plan.splits > 1 && !a->no_spin) {
     // the spinning fix-up makes split CTAs wait for their siblings: every CTA of the grid must be
     // resident at once, at the occupancy this launch really gets (the planner guarantees it; forced
     // test configurations are checked here instead of deadlocking)
-    const int tmem_c = tmem_cols_for(p.BN);
+    const int tmem_c = tmem_cols_for(BN);
     const int occ = (2 * (smem_bytes + 1024) <= 227 * 1024 && 2 * tmem_c <= 512) ? 2 : 1;
-    if ((long long)m_tiles * n_tiles * p.splits > (long long)occ * sm_count()) return EA_ERR_SHAPE;
+    if (tiles * G * plan.splits > (long long)occ * sm_count()) return EA_ERR_SHAPE;
   }
-  static int max_set[2] = {0, 0};
-  if (smem_bytes > max_set[two]) {
-    cudaError_t se = two ? cudaFuncSetAttribute(ea_gemm_kernel<true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
-                         : cudaFuncSetAttribute(ea_gemm_kernel<false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (se != cudaSuccess) return EA_ERR_CUDA;
-    max_set[two] = smem_bytes;
-  }
+  static int cache_k[2][2] = {{0, 0}, {0, 0}};
   cudaError_t le;
+  int rc;
   if (two) {
-    dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, 1);   // whole CTA pairs along M
-    le = ea_launch_cluster(ea_gemm_kernel<true>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 2u,
-                           tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p);
+    dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, (unsigned)G);   // whole CTA pairs along M
+    if (G == 1) {
+      if ((rc = set_max_smem(ea_gemm_kernel<true, 1>, smem_bytes, cache_k[1][0]))) return rc;
+      le = ea_launch_cluster(ea_gemm_kernel<true, 1>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 2u, L1);
+    } else {
+      if ((rc = set_max_smem(ea_gemm_kernel<true, GEMM_MAX_GROUPS>, smem_bytes, cache_k[1][1]))) return rc;
+      le = ea_launch_cluster(ea_gemm_kernel<true, GEMM_MAX_GROUPS>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream,
+                             2u, L);
+    }
   } else {
-    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)p.splits);
-    le = ea_launch(ea_gemm_kernel<false>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream,
-                   tmA[0], tmA[1], tmA[2], tmA[3], tmAx, tmB, p);
+    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)(plan.splits * G));
+    if (G == 1) {
+      if ((rc = set_max_smem(ea_gemm_kernel<false, 1>, smem_bytes, cache_k[0][0]))) return rc;
+      le = ea_launch(ea_gemm_kernel<false, 1>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, L1);
+    } else {
+      if ((rc = set_max_smem(ea_gemm_kernel<false, GEMM_MAX_GROUPS>, smem_bytes, cache_k[0][1]))) return rc;
+      le = ea_launch(ea_gemm_kernel<false, GEMM_MAX_GROUPS>, grid, dim3(GEMM_THREADS), (size_t)smem_bytes, stream, L);
+    }
   }
   ea_count_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
 }
+
+extern "C" int ea_gemm(const ea_gemm_args* a, void* stream) { return ea_gemm_grouped(a, 1, stream); }

@@ -21,15 +21,26 @@ __device__ __forceinline__ int gn_ld_acquire(const int* p) {
   return v;
 }
 
+// Affine parameters per network group: images [g * ipg, (g + 1) * ipg) use gamma[g] / beta[g] (the UNet encoder and the
+// ControlNets run the same layer on stacked activations with their own weights); ipg = 0 -> one set for all images.
+struct GnAffine {
+  const float* gamma[3];
+  const float* beta[3];
+  int ipg;
+};
+
 __global__ void __launch_bounds__(512, 1)
 gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
                 const ea_half* __restrict__ x2, long long ldx2,
-                const float* __restrict__ gamma, const float* __restrict__ beta,
+                const GnAffine aff,
                 ea_half* __restrict__ out, long long ldo, int HW, int C, int groups, float eps,
                 int silu, int chunks, int ppc, int cached, int part_bytes, int phase,
                 float* __restrict__ ws) {
   pdl_launch_dependents();
   pdl_wait();
+  const int net = aff.ipg > 0 ? (int)blockIdx.y / aff.ipg : 0;
+  const float* __restrict__ gamma = net == 0 ? aff.gamma[0] : net == 1 ? aff.gamma[1] : aff.gamma[2];
+  const float* __restrict__ beta = net == 0 ? aff.beta[0] : net == 1 ? aff.beta[1] : aff.beta[2];
   extern __shared__ __align__(16) uint8_t gn_smem[];
   float* sh = reinterpret_cast<float*>(gn_smem);                  // [2*groups]
   float* part = reinterpret_cast<float*>(gn_smem + 512);          // [lanes][2][C] per-lane partials
@@ -777,19 +788,32 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
       return EA_ERR_CUDA;
     max_set = smem;
   }
+  GnAffine aff;
+  aff.gamma[0] = a->gamma; aff.beta[0] = a->beta;
+  aff.gamma[1] = aff.gamma[2] = a->gamma; aff.beta[1] = aff.beta[2] = a->beta;
+  aff.ipg = 0;
+  if (a->n_nets > 1) {
+    if (a->n_nets > 3 || a->B % a->n_nets != 0) return EA_ERR_ARG;
+    for (int g = 1; g < a->n_nets; ++g) {
+      if (!a->gamma_more[g - 1] || !a->beta_more[g - 1]) return EA_ERR_ARG;
+      aff.gamma[g] = a->gamma_more[g - 1];
+      aff.beta[g] = a->beta_more[g - 1];
+    }
+    aff.ipg = a->B / a->n_nets;
+  }
   dim3 grid(chunks, a->B);
   if (a->two_pass) {
     const int smem1 = 512 + part_bytes;
     for (int phase = 1; phase <= 2; ++phase)
       ea_launch(gn_fused_kernel, grid, dim3(threads), (size_t)smem1, st,
                 reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
-                a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
+                a->ldx2, aff, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
                 a->groups, a->eps, a->silu, chunks, ppc, 0, part_bytes, phase, a->workspace);
     ea_count_launch();
     return EA_LAUNCH_OK();
   }
   ea_launch(gn_fused_kernel, dim3(grid), dim3(threads), (size_t)(smem), st, reinterpret_cast<const ea_half*>(a->x), a->ldx, C1, reinterpret_cast<const ea_half*>(a->x2),
-      a->ldx2, a->gamma, a->beta, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
+      a->ldx2, aff, reinterpret_cast<ea_half*>(a->out), a->ldo, a->HW, a->C,
       a->groups, a->eps, a->silu, chunks, ppc, cached, part_bytes, 0, a->workspace);
   return EA_LAUNCH_OK();
 }

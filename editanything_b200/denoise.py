@@ -61,7 +61,19 @@ class DenoiseEngine:
         ctx = ctx.to(self.dev)
         self.B = ctx.shape[0]
         nets = [self.unet] + self.cns
-        caches = [n.precompute_context(ctx) for n in nets]
+        # lockstep (nets.UNetRunner): the encoder-side K/V of all networks live stacked in ctx_ls; only the UNet
+        # (whose decoder runs alone) keeps its own per-layer cache
+        ls = self.runner.lockstep
+        caches = [n.precompute_context(ctx) for n in (nets[:1] if ls else nets)]
+        new_ls = self.runner.precompute_context_lockstep(ctx) if ls else None
+        old_ls = getattr(self, "ctx_ls", None)
+        if ls and old_ls is not None and old_ls["L"] == new_ls["L"] and old_ls["B"] == new_ls["B"]:
+            for k in old_ls["kv"]:
+                old_ls["kv"][k].copy_(new_ls["kv"][k])
+        else:
+            self.ctx_ls = new_ls
+            if ls:
+                self._graph = None
         old = getattr(self, "ctx_cache", None)
         if old is not None and len(old) == len(caches) and all(
                 o["L"] == c["L"] and o["B"] == c["B"] for o, c in zip(old, caches)):
@@ -150,7 +162,7 @@ class DenoiseEngine:
         xh = x_nchw.to(self.dev).permute(0, 2, 3, 1).contiguous().to(self.hdt)
         self._fill_emb(t)
         xn = self.runner.eps_features(xh, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws,
-                                      embs=self.emb_bufs)
+                                      embs=self.emb_bufs, ctx_ls=self.ctx_ls)
         eps = torch.empty(B, H, W_, 4, device=self.dev, dtype=torch.float32)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], eps_out=eps, Nimg=B // 2, H=H,
                               W=W_, C_=self.cfg.model_channels)
@@ -162,7 +174,7 @@ class DenoiseEngine:
         self.ops.step_gather(self.step_ctr, self._sched_cap, [self.coef_tab] + self.emb_tabs,
                              [self.coef_dev] + self.emb_bufs)
         xn = self.runner.eps_features(self.x_half, self.t_dev, self.ctx_cache, self.hints, self.scales, self.gn_ws,
-                                      embs=self.emb_bufs)
+                                      embs=self.emb_bufs, ctx_ls=self.ctx_ls)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], latents=self.lat,
                               coef=self.coef_dev, guidance=self.guidance, known=self.known, noise=self.noise,
                               mask=self.mask, lat_half_out=self.x_half, step_counter=self.step_ctr,

@@ -206,100 +206,174 @@ class PackedNet:
     def _new(self, *shape):
         return torch.empty(*shape, device=self.dev, dtype=self.hdt)
 
-    def _res(self, blk, x, emb_all, gn_ws, out=None, out2=None):
-        """x: NHWC view [B,H,W,cin] (may be a concat buffer).  Returns [B,H,W,cout]."""
-        o, w, p = self.ops, self.w, blk.prefix
+    # block execution lives in BlockRunner (one network or several in lockstep)
+    def _run_layers(self, layers, h, emb_all, ctxc, gn_ws, final_out=None, final_out2=None):
+        return BlockRunner([self])._run_layers(layers, h, [emb_all], ctxc, gn_ws, final_out=final_out,
+                                               final_out2=final_out2)
+
+
+class BlockRunner:
+    """Executes ResBlocks / SpatialTransformers / resampling convolutions for ONE network or for n networks of
+    the same topology in lockstep (the UNet encoder and the ControlNets: cldm/cldm.py:22-45 vs 284-305 - the same
+    layers, different weights, the same latent).  In lockstep the activations are stacked along the batch dimension
+    ([n*B, H, W, C], network g = images [g*B, (g+1)*B)), every GEMM is ONE grouped launch (ea_gemm_grouped: group
+    g = network g's weights on its slice), GroupNorm takes one (gamma, beta) per network, attention simply sees
+    n*B batch entries.  `out2` (the UNet's skip-concat dual store) applies to network 0 only."""
+
+    def __init__(self, nets):
+        self.nets, self.n = list(nets), len(nets)
+        n0 = self.nets[0]
+        self.ops, self.cfg, self.dev, self.hdt, self.ln_fold = n0.ops, n0.cfg, n0.dev, n0.hdt, n0.ln_fold
+        self.emb_off = n0.emb_off
+
+    def _new(self, *shape):
+        return torch.empty(*shape, device=self.dev, dtype=self.hdt)
+
+    def _chunk(self, t, g):
+        return t if self.n == 1 else t.chunk(self.n, 0)[g]
+
+    def gemm(self, a, wkey, out=None, *, bias=None, rowvec=None, residual=None, out2=None, conv=None,
+             rowstats_out=None, ln=None, a_extra=None, M=None, **kw):
+        """bias / ln[1]: weight-dict keys; rowvec: one tensor per network; rowstats_out / ln[0]: [n, C/32, M, 2]."""
+        n, nets = self.n, self.nets
+        if n == 1:
+            w = nets[0].w
+            return self.ops.gemm(a, w[wkey], out, bias=w[bias] if bias else None,
+                                 rowvec=rowvec[0] if rowvec is not None else None, residual=residual, out2=out2,
+                                 conv=conv, rowstats_out=rowstats_out[0] if rowstats_out is not None else None,
+                                 ln=(ln[0][0], w[ln[1]], ln[2]) if ln is not None else None, a_extra=a_extra, M=M, **kw)
+        w0 = nets[0].w[wkey]
+        if out is None:
+            rows = conv[0] * conv[1] * conv[2] if conv is not None else a.shape[0]
+            out = self._new(rows, w0.shape[0] // 2 if kw.get("act") == L.EA_ACT_GEGLU else w0.shape[0])
+        calls = []
+        for g in range(n):
+            w = nets[g].w
+            kwg = dict(kw)
+            kwg["bias"] = w[bias] if bias else None
+            if rowvec is not None:
+                kwg["rowvec"] = rowvec[g]
+            if residual is not None:
+                kwg["residual"] = self._chunk(residual, g)
+            if out2 is not None and g == 0:
+                kwg["out2"] = out2
+            else:
+                kwg.pop("ldo2", None)
+            if conv is not None:
+                kwg["conv"] = (conv[0] // n,) + tuple(conv[1:])
+            if rowstats_out is not None:
+                kwg["rowstats_out"] = rowstats_out[g]
+            if ln is not None:
+                kwg["ln"] = (ln[0][g], w[ln[1]], ln[2])
+            if a_extra is not None:
+                kwg["a_extra"] = self._chunk(a_extra, g)
+            if M is not None:
+                kwg["M"] = M // n
+            calls.append((self._chunk(a, g), w[wkey], self._chunk(out, g), kwg))
+        self.ops.gemm_grouped(calls)
+        return out
+
+    def groupnorm(self, x, key, out, **kw):
+        if self.n == 1:
+            w = self.nets[0].w
+            return self.ops.groupnorm(x, w[key + ".g"], w[key + ".b"], out, **kw)
+        return self.ops.groupnorm(x, [nt.w[key + ".g"] for nt in self.nets], [nt.w[key + ".b"] for nt in self.nets],
+                                  out, **kw)
+
+    def _res(self, blk, x, embs, gn_ws, out=None, out2=None):
+        """x: NHWC view [B,H,W,cin] (may be a concat buffer).  Returns [B,H,W,cout].  embs: one [B, emb_total]
+        row-vector table per network."""
+        p = blk.prefix
         B, H, W_, cin = x.shape
         cout = blk.cout
         a1 = self._new(B, H, W_, cin)
-        o.groupnorm(x, w[p + ".in_layers.0.g"], w[p + ".in_layers.0.b"], a1, B=B, HW=H * W_, C_=cin, eps=1e-5,
-                    silu=True, workspace=gn_ws, ldx=x.stride(2))
+        self.groupnorm(x, p + ".in_layers.0", a1, B=B, HW=H * W_, C_=cin, eps=1e-5, silu=True, workspace=gn_ws,
+                       ldx=x.stride(2))
         h1 = self._new(B, H, W_, cout)
         off = self.emb_off[p]
-        o.gemm(a1, w[p + ".conv1.w"], h1, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cin),
-               rowvec=emb_all[:, off:off + cout])
+        self.gemm(a1, p + ".conv1.w", h1, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cin),
+                  rowvec=[e[:, off:off + cout] for e in embs])
         a2 = self._new(B, H, W_, cout)
-        o.groupnorm(h1, w[p + ".out_layers.0.g"], w[p + ".out_layers.0.b"], a2, B=B, HW=H * W_, C_=cout, eps=1e-5,
-                    silu=True, workspace=gn_ws)
+        self.groupnorm(h1, p + ".out_layers.0", a2, B=B, HW=H * W_, C_=cout, eps=1e-5, silu=True, workspace=gn_ws)
         if out is None:
             out = self._new(B, H, W_, cout)
         if cin != cout:
-            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout), a_extra=x,
-                   ld_extra=x.stride(2), bias=w[p + ".conv2.b"], out2=out2)
+            self.gemm(a2, p + ".conv2.w", out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout), a_extra=x,
+                      ld_extra=x.stride(2), bias=p + ".conv2.b", out2=out2)
         else:
-            o.gemm(a2, w[p + ".conv2.w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout),
-                   bias=w[p + ".conv2.b"], residual=x, out2=out2)
+            self.gemm(a2, p + ".conv2.w", out, mode=L.EA_GEMM_CONV_S1, conv=(B, H, W_, cout),
+                      bias=p + ".conv2.b", residual=x, out2=out2)
         return out
 
     def _attn(self, blk, x, ctxc, gn_ws, out=None, out2=None):
-        o, w, p = self.ops, self.w, blk.prefix
+        o, p, n = self.ops, blk.prefix, self.n
         B, H, W_, c = x.shape
         heads, dh = self.cfg.heads_for(c)
         inner = heads * dh
         N, M = H * W_, B * H * W_
         xn = self._new(B, H, W_, c)
-        o.groupnorm(x, w[p + ".norm.g"], w[p + ".norm.b"], xn, B=B, HW=N, C_=c, eps=1e-6, silu=False,
-                    workspace=gn_ws, ldx=x.stride(2))
+        self.groupnorm(x, p + ".norm", xn, B=B, HW=N, C_=c, eps=1e-6, silu=False, workspace=gn_ws, ldx=x.stride(2))
         fold = self.ln_fold
 
         def stats():   # per-row partial (sum, sumsq) per 32-column chunk, written by the producing GEMM
-            return torch.empty(inner // 32, M, 2, device=self.dev, dtype=torch.float32) if fold else None
+            return torch.empty(n, inner // 32, M // n, 2, device=self.dev, dtype=torch.float32) if fold else None
 
         def normed(t, st, name, nrm, **kw):   # GEMM on LayerNorm(t): folded, or LayerNorm launch + plain GEMM
             if fold:
-                return o.gemm(t, w[f"{p}.{name}.w"], bias=w[f"{p}.{name}.b"], ln=(st, w[f"{p}.{name}.g"], 1e-5), **kw)
-            n = self._new(M, inner)
-            o.layernorm(t, w[f"{p}.{nrm}.g"], w[f"{p}.{nrm}.b"], n, M=M, C_=inner)
-            return o.gemm(n, w[f"{p}.{name}.w"], bias=w.get(f"{p}.{name}.b"), **kw)
+                return self.gemm(t, f"{p}.{name}.w", bias=f"{p}.{name}.b", ln=(st, f"{p}.{name}.g", 1e-5), **kw)
+            w = self.nets[0].w                 # (lockstep needs the fold: UNetRunner checks)
+            nn_ = self._new(M, inner)
+            o.layernorm(t, w[f"{p}.{nrm}.g"], w[f"{p}.{nrm}.b"], nn_, M=M, C_=inner)
+            return self.gemm(nn_, f"{p}.{name}.w", bias=f"{p}.{name}.b" if f"{p}.{name}.b" in w else None, **kw)
 
         st0, st1, st2 = stats(), stats(), stats()
-        t0 = o.gemm(xn.view(M, c), w[p + ".proj_in.w"], bias=w[p + ".proj_in.b"], rowstats_out=st0)
+        t0 = self.gemm(xn.view(M, c), p + ".proj_in.w", bias=p + ".proj_in.b", rowstats_out=st0)
         qkv = normed(t0, st0, "qkv1", "norm1")                  # [M, 3*inner]
         ao = self._new(M, inner)
         o.attention(qkv, qkv[:, inner:], qkv[:, 2 * inner:], ao, B=B, heads=heads, Nq=N, Nkv=N, d=dh,
                     q_strides=(N * 3 * inner, 3 * inner), k_strides=(N * 3 * inner, 3 * inner),
                     v_strides=(N * 3 * inner, 3 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
-        t1 = o.gemm(ao, w[p + ".o1.w"], bias=w[p + ".o1.b"], residual=t0, rowstats_out=st1)
+        t1 = self.gemm(ao, p + ".o1.w", bias=p + ".o1.b", residual=t0, rowstats_out=st1)
         q2 = normed(t1, st1, "q2", "norm2")
-        kv = ctxc["kv"][p]
+        kv = ctxc["kv"][p]                                       # [B*L, 2*inner] (stacked like x in lockstep)
         Lc = ctxc["L"]
         ao2 = self._new(M, inner)
         o.attention(q2, kv, kv[:, inner:], ao2, B=B, heads=heads, Nq=N, Nkv=Lc, d=dh,
                     q_strides=(N * inner, inner), k_strides=(Lc * 2 * inner, 2 * inner),
                     v_strides=(Lc * 2 * inner, 2 * inner), o_strides=(N * inner, inner), scale=dh ** -0.5)
-        t2 = o.gemm(ao2, w[p + ".o2.w"], bias=w[p + ".o2.b"], residual=t1, rowstats_out=st2)
+        t2 = self.gemm(ao2, p + ".o2.w", bias=p + ".o2.b", residual=t1, rowstats_out=st2)
         g = normed(t2, st2, "ff1", "norm3", act=L.EA_ACT_GEGLU)   # [M, 4*inner]
-        t3 = o.gemm(g, w[p + ".ff2.w"], bias=w[p + ".ff2.b"], residual=t2)
+        t3 = self.gemm(g, p + ".ff2.w", bias=p + ".ff2.b", residual=t2)
         if out is None:
             out = self._new(B, H, W_, c)
-        o.gemm(t3, w[p + ".proj_out.w"], out.view(M, -1) if out.is_contiguous() else out, M=M, bias=w[p + ".proj_out.b"],
-               residual=x, ldr=x.stride(2), ldo=out.stride(2), out2=out2,
-               ldo2=(out2.stride(2) if out2 is not None else None))
+        self.gemm(t3, p + ".proj_out.w", out.view(M, -1) if out.is_contiguous() else out, M=M, bias=p + ".proj_out.b",
+                  residual=x, ldr=x.stride(2), ldo=out.stride(2), out2=out2,
+                  ldo2=(out2.stride(2) if out2 is not None else None))
         return out
 
-    def _run_layers(self, layers, h, emb_all, ctxc, gn_ws, final_out=None, final_out2=None):
+    def _run_layers(self, layers, h, embs, ctxc, gn_ws, final_out=None, final_out2=None):
         """Run one TimestepEmbedSequential; the LAST operator writes to final_out / final_out2."""
-        o, w = self.ops, self.w
+        o = self.ops
         for i, blk in enumerate(layers):
             last = i == len(layers) - 1
             fo = final_out if last else None
             fo2 = final_out2 if last else None
             B, H, W_, _ = h.shape
             if blk.kind == "res":
-                h = self._res(blk, h, emb_all, gn_ws, out=fo, out2=fo2)
+                h = self._res(blk, h, embs, gn_ws, out=fo, out2=fo2)
             elif blk.kind == "attn":
                 h = self._attn(blk, h, ctxc, gn_ws, out=fo, out2=fo2)
             elif blk.kind == "down":
                 out = fo if fo is not None else self._new(B, H // 2, W_ // 2, blk.cout)
-                o.gemm(h, w[blk.prefix + ".w"], out, mode=L.EA_GEMM_CONV_S2, conv=(B, H // 2, W_ // 2, blk.cin),
-                       bias=w[blk.prefix + ".b"], out2=fo2)
+                self.gemm(h, blk.prefix + ".w", out, mode=L.EA_GEMM_CONV_S2, conv=(B, H // 2, W_ // 2, blk.cin),
+                          bias=blk.prefix + ".b", out2=fo2)
                 h = out
             elif blk.kind == "up":
                 up = self._new(B, 2 * H, 2 * W_, blk.cin)
                 o.upsample2x(h, up, B=B, H=H, W=W_, C_=blk.cin)
                 out = fo if fo is not None else self._new(B, 2 * H, 2 * W_, blk.cout)
-                o.gemm(up, w[blk.prefix + ".w"], out, mode=L.EA_GEMM_CONV_S1, conv=(B, 2 * H, 2 * W_, blk.cin),
-                       bias=w[blk.prefix + ".b"], out2=fo2)
+                self.gemm(up, blk.prefix + ".w", out, mode=L.EA_GEMM_CONV_S1, conv=(B, 2 * H, 2 * W_, blk.cin),
+                          bias=blk.prefix + ".b", out2=fo2)
                 h = out
             else:
                 raise ValueError(blk.kind)
@@ -313,10 +387,16 @@ class UNetRunner:
         self.unet, self.cns, self.dev = unet, list(controlnets), device
         self.ops = unet.ops
         self.hdt = unet.hdt
-        import os
         self.concurrent = os.environ.get("EA_CONCURRENT", "1") != "0"
         self._streams = []
         self._lane_gn = {}
+        # Lockstep: the UNet encoder and the ControlNets as ONE sequence of grouped launches (BlockRunner) instead of
+        # one stream per network.  Needs identical topologies, the LayerNorm fold and at most 3 networks
+        # (ea_gemm_grouped); EA_LOCKSTEP=0 falls back to the concurrent streams (A/B).
+        nets = [unet] + self.cns
+        self.lockstep = (os.environ.get("EA_LOCKSTEP", "1") != "0" and 2 <= len(nets) <= 3 and unet.ln_fold
+                         and all(n.cfg == unet.cfg and n.ln_fold for n in nets) and hasattr(self.ops, "gemm_grouped"))
+        self._ls_ws = {}
 
     def _lane_ws(self, B, n):
         """One zeroed GroupNorm workspace per concurrent stream."""
@@ -376,6 +456,76 @@ class UNetRunner:
                        accumulate=True, ldo=mid_sink.stride(2))
         return h
 
+    def precompute_context_lockstep(self, ctx):
+        """Cross-attention K/V of the encoder + middle attention layers of every network, stacked along the batch
+        like the lockstep activations: kv[p] = [n * B * L, 2 * inner] (network g = rows [g*B*L, (g+1)*B*L))."""
+        nets = [self.unet] + self.cns
+        n = len(nets)
+        B, Lc, D = ctx.shape
+        ctx2 = ctx.to(self.hdt).reshape(B * Lc, D).contiguous()
+        topo = self.unet.topo
+        kv = {}
+        for layers in list(topo.input_blocks) + [topo.middle]:
+            for b in layers:
+                if b.kind == "attn":
+                    p = b.prefix
+                    out = torch.empty(n * B * Lc, self.unet.w[p + ".kv2.w"].shape[0], device=self.dev, dtype=self.hdt)
+                    self.ops.gemm_grouped([(ctx2, nt.w[p + ".kv2.w"], out.chunk(n, 0)[g], {}) for g, nt in enumerate(nets)])
+                    kv[p] = out
+        return {"kv": kv, "B": n * B, "L": Lc}
+
+    def _encoder_lockstep(self, x_half, embs, ctx_ls, hints, sinks, scales):
+        """input_blocks + middle of the UNet and every ControlNet in lockstep (see BlockRunner).  The UNet's skips are
+        dual-stored into the decoder's concat slots by the grouped launch itself (out2, network 0); each ControlNet's
+        zero-conv then accumulates `scale * zero_conv(h)` into the same slot (cldm/cldm.py:34-41,293-303)."""
+        o = self.ops
+        un = self.unet
+        nets = [un] + self.cns
+        n = len(nets)
+        R = BlockRunner(nets)
+        topo = un.topo
+        B, H, W_, _ = x_half.shape
+        key = (n * B,)
+        if key not in self._ls_ws:
+            self._ls_ws[key] = torch.zeros(n * B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
+        gn_ws = self._ls_ws[key]
+
+        def zero_convs(h, i, slot):
+            c = h.shape[-1]
+            Mg = B * h.shape[1] * h.shape[2]
+            for k, cn in enumerate(self.cns):
+                pz = f"zero_convs.{i}.0" if i is not None else "mid_out"
+                wz, bz = (cn.w[pz + ".w"], cn.w[pz + ".b"])
+                o.gemm(h.chunk(n, 0)[1 + k].reshape(Mg, c), wz, slot, M=Mg, bias=bz, out_scale=float(scales[k]),
+                       accumulate=True, ldo=slot.stride(2))
+
+        h = None
+        for i, layers in enumerate(topo.input_blocks):
+            slot = sinks["skip"][i]
+            if layers[0].kind == "conv_in":
+                blk = layers[0]
+                h = R._new(n * B, H, W_, blk.cout)
+                for g, nt in enumerate(nets):
+                    hg = h.chunk(n, 0)[g]
+                    w = nt.w
+                    if blk.cin in (4, 8):
+                        o.conv_in(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], hg, B=B, H=H, W=W_, Cin=blk.cin,
+                                  Cout=blk.cout, out2=slot if g == 0 else None, ldo2=slot.stride(2) if g == 0 else 0,
+                                  add=hints[g - 1] if g > 0 else None)
+                    else:
+                        o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], hg, B=B, Hin=H, Win=W_,
+                                      Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, add=hints[g - 1] if g > 0 else None)
+                        if g == 0:
+                            o.conv_direct(x_half, w[blk.prefix + ".w"], w[blk.prefix + ".b"], slot, B=B, Hin=H, Win=W_,
+                                          Cin=blk.cin, Cout=blk.cout, ksize=3, stride=1, ldo=slot.stride(2))
+            else:
+                h = R._run_layers(layers, h, embs, ctx_ls, gn_ws, final_out2=slot)
+            zero_convs(h, i, slot)
+        mid_sink = sinks["mid"]
+        h = R._run_layers(topo.middle, h, embs, ctx_ls, gn_ws, final_out2=mid_sink)
+        zero_convs(h, None, mid_sink)
+        return h
+
     def alloc_sinks(self, B, H, W_):
         """Skip-concat buffers of the decoder: cat_i = [h (C1) | skip_i + control_i (C2)]."""
         topo = self.unet.topo
@@ -405,7 +555,7 @@ class UNetRunner:
         per timestep instead of re-streaming ~93 MB of embedding weights every step."""
         return [n._emb(t_dev, B) for n in [self.unet] + self.cns]
 
-    def eps_features(self, x_half, t_dev, ctx_cache, hints, scales, gn_ws=None, embs=None):
+    def eps_features(self, x_half, t_dev, ctx_cache, hints, scales, gn_ws=None, embs=None, ctx_ls=None):
         """Runs UNet encoder, ControlNets, UNet decoder; returns the GroupNorm+SiLU'd input of the
         final convolution [B,H,W,mc] (the out conv itself is fused with CFG/DDIM)."""
         un = self.unet
@@ -418,7 +568,11 @@ class UNetRunner:
             embs = self.compute_embs(t_dev, B)
         emb_u = embs[0]
         concurrent = self.concurrent and len(self.cns) > 0 and hasattr(o, "set_lane") and x_half.is_cuda
-        if concurrent:
+        if self.lockstep and ctx_ls is not None:
+            if hasattr(o, "set_lane"):
+                o.set_lane(0, False)
+            self._encoder_lockstep(x_half, embs, ctx_ls, hints, sinks, scales)
+        elif concurrent:
             # The UNet encoder and every ControlNet only READ x and write their own activations: run
             # them on parallel streams (many of their launches cannot fill 148 SMs on their own), join,
             # then apply the zero-conv accumulations into the shared skip slots on the main stream.

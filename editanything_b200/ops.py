@@ -57,16 +57,12 @@ def gemm_workspace(device):
     return ws
 
 
-def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
-         conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
-         out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
-         ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0,
-         force_persistent=0, rowstats_out=None, ln=None):
-    """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes.
-    rowstats_out: fp32 [N/32, M, 2] per-row partial (sum, sumsq) of the stored values (LayerNorm fold, producer);
-    ln = (stats [K/32, M, 2], g [N], eps): the consumer side - `w` is W*gamma, `bias` is W beta + b."""
-    lib = L.lib()
-    g = L.GemmArgs()
+def _fill_gemm(g, a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=None, ldw=0,
+               conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
+               out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
+               ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0,
+               force_persistent=0, rowstats_out=None, ln=None):
+    """Fills one ea_gemm_args; returns the output tensor (allocated when the caller gave none)."""
     g.mode = mode
     g.N = N if N is not None else w.shape[0]
     if mode == L.EA_GEMM_LINEAR:
@@ -123,8 +119,29 @@ def gemm(a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=None, lda=N
     ws = gemm_workspace(a.device)
     g.workspace = ws.data_ptr()
     g.workspace_bytes = ws.numel()
-    L.check(lib.ea_gemm(C.byref(g), _stream()), "ea_gemm")
     return out if out is not None else out_f32
+
+
+def gemm(a, w, out=None, **kw):
+    """out = epilogue(A @ W^T).  conv = (B, H, W, Cin) output-space geometry for CONV modes.
+    rowstats_out: fp32 [N/32, M, 2] per-row partial (sum, sumsq) of the stored values (LayerNorm fold, producer);
+    ln = (stats [K/32, M, 2], g [N], eps): the consumer side - `w` is W*gamma, `bias` is W beta + b."""
+    lib = L.lib()
+    g = L.GemmArgs()
+    res = _fill_gemm(g, a, w, out, **kw)
+    L.check(lib.ea_gemm(C.byref(g), _stream()), "ea_gemm")
+    return res
+
+
+def gemm_grouped(calls):
+    """calls: list (1..3) of (a, w, out, kwargs) with the same shape and flags - ONE launch (ea_gemm_grouped).
+    Returns the list of outputs."""
+    lib = L.lib()
+    n = len(calls)
+    arr = (L.GemmArgs * n)()
+    outs = [_fill_gemm(arr[i], a, w, out, **kw) for i, (a, w, out, kw) in enumerate(calls)]
+    L.check(lib.ea_gemm_grouped(arr, n, _stream()), "ea_gemm_grouped")
+    return outs
 
 
 def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_strides, o_strides,
@@ -155,6 +172,11 @@ def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True,
         g.x2 = x2.data_ptr()
         g.C1 = C1
         g.ldx2 = ldx2 if ldx2 is not None else (C_ - C1)
+    if isinstance(gamma, (list, tuple)):     # one (gamma, beta) per stacked network (ea_gn_args.n_nets)
+        g.n_nets = len(gamma)
+        for i in range(1, len(gamma)):
+            g.gamma_more[i - 1], g.beta_more[i - 1] = gamma[i].data_ptr(), beta[i].data_ptr()
+        gamma, beta = gamma[0], beta[0]
     g.gamma, g.beta = gamma.data_ptr(), beta.data_ptr()
     g.out = out.data_ptr()
     g.ldo = ldo if ldo is not None else C_

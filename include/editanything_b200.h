@@ -131,6 +131,13 @@ typedef struct ea_gemm_args {
                                 is never split.  One workspace may serve every call on a stream. */
 } ea_gemm_args;
 int ea_gemm(const ea_gemm_args* args, void* stream);
+/* ea_gemm_grouped: n_groups (1..3) problems of the SAME shape, epilogue flags and force_* fields - only the
+ * pointers (and leading dimensions, out_scale) differ - as ONE launch: the UNet encoder and the ControlNets are the
+ * same network with different weights applied to the same latent (cldm/cldm.py:22-45 vs 284-305), so every layer of
+ * the three runs as one grid three times as large instead of three latency-bound launches.  The launch plan is
+ * chosen once for all groups; args[0].workspace serves every group.  ea_gemm(a, s) == ea_gemm_grouped(a, 1, s).
+ * Not re-entrant: one caller per process at a time (host-side staging of the parameter block is static). */
+int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* stream);
 /* Diagnostic (no GPU needed): the launch plan ea_gemm would choose for m_tiles x N with k_blocks
  * 64-wide K-blocks: out5 = {BN, stages, splits, k_blocks_per_split, CTAs_per_SM}. */
 int ea_gemm_plan(int m_tiles, int N, int k_blocks, int act, long long workspace_bytes, int n_sm,
@@ -172,6 +179,11 @@ typedef struct ea_gn_args {
                                 (required when other streams run kernels concurrently) */
   float* workspace;          /* >= B*(2*groups+2) floats, ZERO before the first call (the kernel
                                 leaves it zero); one workspace may serve every call on a stream */
+  int n_nets;                /* 0 / 1: one gamma / beta for all B images.  2 / 3: the images are n_nets stacked
+                                batches of B / n_nets (the same layer of the UNet encoder and the ControlNets,
+                                see ea_gemm_grouped); batch g > 0 uses gamma_more[g-1] / beta_more[g-1] */
+  const float* gamma_more[2];
+  const float* beta_more[2];
 } ea_gn_args;
 int ea_groupnorm(const ea_gn_args* args, void* stream);
 int ea_layernorm(const void* x, long long ldx, const float* gamma, const float* beta, void* out,

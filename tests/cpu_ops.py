@@ -88,6 +88,10 @@ def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, con
     return tgt
 
 
+def gemm_grouped(calls):
+    return [gemm(a, w, out, **kw) for a, w, out, kw in calls]
+
+
 def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_strides, o_strides, scale,
               rel_h=None, rel_w=None, rel_s=0):
     _bump()
@@ -113,7 +117,13 @@ def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True,
     xs = x.reshape(B, HW, -1).float()
     if x2 is not None:
         xs = torch.cat([xs, x2.reshape(B, HW, -1).float()], -1)
-    y = F.group_norm(xs.permute(0, 2, 1), groups, gamma, beta, eps).permute(0, 2, 1)
+    if isinstance(gamma, (list, tuple)):       # stacked networks: images [g*B/n, (g+1)*B/n) use gamma[g] / beta[g]
+        n = len(gamma)
+        ipg = B // n
+        y = torch.cat([F.group_norm(xs[g * ipg:(g + 1) * ipg].permute(0, 2, 1), groups, gamma[g], beta[g], eps)
+                       for g in range(n)]).permute(0, 2, 1)
+    else:
+        y = F.group_norm(xs.permute(0, 2, 1), groups, gamma, beta, eps).permute(0, 2, 1)
     if silu:
         y = F.silu(y)
     out.copy_(y.reshape(out.shape))

@@ -622,6 +622,109 @@ def case_step_gather_and_renoised_blend():
     return {"max_abs": worst / 10, "ref_max": 1.0}
 
 
+def _grouped_case(kind, seed=31, **force):
+    """ea_gemm_grouped (3 networks, one launch) against three separate ea_gemm launches with the same plan:
+    every output element is computed with the same K order, so the results must be bit-identical."""
+    import torch
+    from editanything_b200 import ops, _lib as L
+    dt = ops.half_dtype()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n = 3
+    calls_a, calls_b = [], []
+    outs_a, outs_b = [], []
+    if kind == "linear":
+        M, N, K = 2048, 640, 640
+        for i in range(n):
+            a = torch.randn(M, K, device="cuda", generator=g).to(dt)
+            w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(dt)
+            b = torch.randn(N, device="cuda", generator=g)
+            r = torch.randn(M, N, device="cuda", generator=g).to(dt)
+            o2 = torch.zeros(M, N, device="cuda", dtype=dt) if i == 0 else None
+            kw = dict(bias=b, residual=r, **force)
+            oa, ob = torch.full((M, N), 7.0, device="cuda", dtype=dt), torch.full((M, N), 7.0, device="cuda", dtype=dt)
+            calls_a.append((a, w, oa, dict(kw, out2=o2) if o2 is not None else kw))
+            calls_b.append((a, w, ob, kw))
+            outs_a.append(oa); outs_b.append(ob)
+    elif kind == "geglu":
+        M, N, K = 2048, 5120, 640
+        for i in range(n):
+            a = torch.randn(M, K, device="cuda", generator=g).to(dt)
+            w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(dt)
+            b = torch.randn(N, device="cuda", generator=g)
+            kw = dict(bias=b, act=L.EA_ACT_GEGLU, **force)
+            oa, ob = torch.full((M, N // 2), 7.0, device="cuda", dtype=dt), torch.full((M, N // 2), 7.0, device="cuda", dtype=dt)
+            calls_a.append((a, w, oa, kw)); calls_b.append((a, w, ob, kw))
+            outs_a.append(oa); outs_b.append(ob)
+    else:   # conv: 3x3 stride 1 with the time-embedding row vector; "conv8" = the split-K 8x8 level
+        B, H, C, Cout = (2, 8, 1280, 1280) if kind == "conv8" else (2, 32, 640, 640)
+        for i in range(n):
+            x = torch.randn(B, H, H, C, device="cuda", generator=g).to(dt)
+            w = (torch.randn(Cout, 9 * C, device="cuda", generator=g) / (9 * C) ** 0.5).to(dt)
+            rv = torch.randn(B, Cout, device="cuda", generator=g)
+            kw = dict(mode=L.EA_GEMM_CONV_S1, conv=(B, H, H, C), rowvec=rv, **force)
+            oa = torch.full((B * H * H, Cout), 7.0, device="cuda", dtype=dt)
+            ob = torch.full((B * H * H, Cout), 7.0, device="cuda", dtype=dt)
+            calls_a.append((x, w, oa, kw)); calls_b.append((x, w, ob, kw))
+            outs_a.append(oa); outs_b.append(ob)
+    ops.gemm_grouped(calls_a)
+    for a, w, o, kw in calls_b:
+        ops.gemm(a, w, o, **kw)
+    torch.cuda.synchronize()
+    worst = max((x.float() - y.float()).abs().max().item() for x, y in zip(outs_a, outs_b))
+    ref_chk = _err(outs_b[1], calls_b[1][0].float() @ calls_b[1][1].float().t() + calls_b[1][3]["bias"] + calls_b[1][3]["residual"].float()) \
+        if kind == "linear" else {"max_abs": 0.0}
+    o2_ok = kind != "linear" or torch.equal(calls_a[0][3]["out2"], outs_a[0])
+    return {"max_abs": worst * 100 + ref_chk["max_abs"] + (0.0 if o2_ok else 1.0), "ref_max": 1.0}
+
+
+def case_grouped_linear():
+    return _grouped_case("linear", force_persistent=-1)
+
+
+def case_grouped_linear_persistent():
+    return _grouped_case("linear", seed=32, force_persistent=2)
+
+
+def case_grouped_linear_2cta():
+    return _grouped_case("linear", seed=33, force_persistent=-1, force_2cta=1)
+
+
+def case_grouped_geglu_persistent():
+    return _grouped_case("geglu", seed=34, force_persistent=2)
+
+
+def case_grouped_geglu():
+    return _grouped_case("geglu", seed=35, force_persistent=-1)
+
+
+def case_grouped_conv():
+    return _grouped_case("conv32", seed=36)
+
+
+def case_grouped_conv_splitk():
+    return _grouped_case("conv8", seed=37)
+
+
+def case_groupnorm_stacked_nets():
+    """ea_groupnorm with one (gamma, beta) per stacked network (ea_gn_args.n_nets)."""
+    import torch
+    import torch.nn.functional as F
+    from editanything_b200 import ops
+    dt = ops.half_dtype()
+    torch.manual_seed(12)
+    n, B, H, C_ = 3, 2, 16, 320
+    x = (torch.randn(n * B, H, H, C_, device="cuda") * 1.5 + 0.3).to(dt)
+    gam = [1 + 0.2 * torch.randn(C_, device="cuda") for _ in range(n)]
+    bet = [0.2 * torch.randn(C_, device="cuda") for _ in range(n)]
+    out = torch.empty_like(x)
+    ws = torch.zeros(n * B * 66, device="cuda")
+    ops.groupnorm(x, gam, bet, out, B=n * B, HW=H * H, C_=C_, eps=1e-5, silu=True, workspace=ws)
+    torch.cuda.synchronize()
+    xs = x.float().permute(0, 3, 1, 2)
+    ref = torch.cat([F.silu(F.group_norm(xs[g * B:(g + 1) * B], 32, gam[g], bet[g], 1e-5)) for g in range(n)]).permute(0, 2, 3, 1)
+    return _err(out, ref)
+
+
 def case_sam_helpers():
     import torch
     from editanything_b200 import ops
