@@ -1003,7 +1003,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   const uint32_t acc_cols = tmem_cols_for(p.BN);
 
   if (warp == PW_TMA && lane == 0) {
-    const int g0 = NG == 1 ? 0 : ((int)blockIdx.x / tiles_per_group) % NG;
+    const int g0 = NG == 1 ? 0 : min((int)blockIdx.x / tiles_per_group, n_groups - 1);
     tma_prefetch_desc(&L.g[g0].tmA0);
     tma_prefetch_desc(&L.g[g0].tmB);
     if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
