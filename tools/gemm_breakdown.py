@@ -22,15 +22,20 @@ def time_group(recs, min_launches=60):
     reps = max(1, (min_launches + len(recs) - 1) // len(recs))
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
+    def issue(r):
+        if r[0] == "grouped":
+            ops.gemm_grouped(r[1])
+        else:
+            ops.gemm(r[0], r[1], r[2], **r[3])
     with torch.cuda.stream(s):
-        for a, w, out, kw, _ in recs:
-            ops.gemm(a, w, out, **kw)
+        for r in recs:
+            issue(r)
     torch.cuda.current_stream().wait_stream(s)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(reps):
-            for a, w, out, kw, _ in recs:
-                ops.gemm(a, w, out, **kw)
+            for r in recs:
+                issue(r)
     g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,6 +62,7 @@ def main():
     eng.ops = eng.runner.ops = eng.unet.ops = probe
     for c in eng.cns:
         c.ops = probe
+    eng.runner.ops = probe
     eng.step(int(ts[0]), float(a[0]), float(ap[0]))
     probe.records.clear()
     eng.step(int(ts[1]), float(a[1]), float(ap[1]))
@@ -64,13 +70,20 @@ def main():
     ops.set_lane(0, False)
     groups = {}
     for r in probe.records:
-        a_, w_, out, kw, fl = r
+        G = 1
+        if r[0] == "grouped":
+            G = len(r[1])
+            a_, w_, out, kw = r[1][0]
+            fl = r[4]
+        else:
+            a_, w_, out, kw, fl = r
         conv = kw.get("conv")
         mode = kw.get("mode", L.EA_GEMM_LINEAR)
         M = conv[0] * conv[1] * conv[2] if conv else (kw.get("M") or a_.shape[0])
         key = (mode, M, w_.shape[0], w_.shape[1], kw.get("act", 0), kw.get("residual") is not None,
                bool(kw.get("accumulate")), kw.get("rowvec") is not None, kw.get("out2") is not None,
-               kw.get("a_extra") is not None, kw.get("out_f32") is not None)
+               kw.get("a_extra") is not None, kw.get("out_f32") is not None, G, kw.get("ln") is not None,
+               kw.get("rowstats_out") is not None)
         groups.setdefault(key, []).append(r)
     rows = []
     lib = L.lib()
@@ -78,10 +91,11 @@ def main():
     for key, recs in groups.items():
         us = time_group(recs)
         mode, M, N, K = key[:4]
-        conv = recs[0][3].get("conv")
+        kw0 = recs[0][1][0][3] if recs[0][0] == "grouped" else recs[0][3]
+        conv = kw0.get("conv")
         if conv:
             cin = conv[3]
-            ex = recs[0][3].get("a_extra")
+            ex = kw0.get("a_extra")
             kb = 9 * ((cin + 63) // 64) + (9 * ((ex.shape[-1] + 63) // 64) if ex is not None else 0)
             if mode == getattr(L, "EA_GEMM_CONV1X1", -99):
                 kb = (cin + 63) // 64
@@ -91,7 +105,8 @@ def main():
         lib.ea_gemm_plan((M + 127) // 128, N, kb, key[4], ops.GEMM_WS_BYTES - 65536, n_sm, out5)
         fl = recs[0][4]
         rows.append({"mode": mode, "M": M, "N": N, "K": K, "act": key[4], "res": key[5], "acc": key[6], "rowvec": key[7],
-                     "out2": key[8], "extra": key[9], "f32": key[10], "n": len(recs), "us": round(us, 2),
+                     "out2": key[8], "extra": key[9], "f32": key[10], "groups": key[11], "ln": key[12], "stats": key[13],
+                     "n": len(recs), "us": round(us, 2),
                      "tflops": round(fl / us / 1e6, 1), "total_ms": round(us * len(recs) / 1e3, 3), "kb": kb,
                      "plan": list(out5)})
     rows.sort(key=lambda r: -r["total_ms"])
@@ -99,13 +114,14 @@ def main():
         json.dump(rows, open(sys.argv[1], "w"), indent=0)
     tot = sum(r["total_ms"] for r in rows)
     print(f"{len(probe.records)} gemm launches, {len(rows)} signatures, sum of isolated times {tot:.3f} ms")
-    print("mode      M     N      K act res acc  n      us  TFLOP/s  total_ms  cum%  kb plan[bn,stages,splits,occ,two]")
+    print("mode      M     N      K act res acc  n      us  TFLOP/s  total_ms  cum%  kb plan[bn,stages,splits,occ,two] (xG = grouped launch of G networks; plan shown for one group)")
     cum = 0.0
     for r in rows:
         cum += r["total_ms"]
         print(f"{r['mode']:3d} {r['M']:6d} {r['N']:5d} {r['K']:6d} {r['act']:3d} {int(r['res']):3d} {int(r['acc']):3d} {r['n']:3d} "
               f"{r['us']:7.2f} {r['tflops']:8.1f} {r['total_ms']:9.3f} {100 * cum / tot:5.1f} {r['kb']:4d} {r['plan']}"
-              f"{' x' if r['extra'] else ''}{' rv' if r['rowvec'] else ''}{' o2' if r['out2'] else ''}{' f32' if r['f32'] else ''}")
+              f"{' x' if r['extra'] else ''}{' rv' if r['rowvec'] else ''}{' o2' if r['out2'] else ''}{' f32' if r['f32'] else ''}"
+              f"{' x' + str(r['groups']) + 'G' if r['groups'] > 1 else ''}{' ln' if r['ln'] else ''}{' st' if r['stats'] else ''}")
 
 
 if __name__ == "__main__":

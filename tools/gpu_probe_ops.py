@@ -671,10 +671,16 @@ def _grouped_case(kind, seed=31, **force):
         ops.gemm(a, w, o, **kw)
     torch.cuda.synchronize()
     worst = max((x.float() - y.float()).abs().max().item() for x, y in zip(outs_a, outs_b))
-    ref_chk = _err(outs_b[1], calls_b[1][0].float() @ calls_b[1][1].float().t() + calls_b[1][3]["bias"] + calls_b[1][3]["residual"].float()) \
-        if kind == "linear" else {"max_abs": 0.0}
     o2_ok = kind != "linear" or torch.equal(calls_a[0][3]["out2"], outs_a[0])
-    return {"max_abs": worst * 100 + ref_chk["max_abs"] + (0.0 if o2_ok else 1.0), "ref_max": 1.0}
+    if kind == "conv8":
+        # K is split over the SMs that are left: three networks in one launch get a different split count than
+        # one network alone, i.e. another fp32 summation order - compare with one output rounding of slack
+        return {"max_abs": worst, "ref_max": max(o.float().abs().max().item() for o in outs_b)}
+    ref = calls_b[1][0].float() @ calls_b[1][1].float().t() + calls_b[1][3]["bias"] + calls_b[1][3]["residual"].float() \
+        if kind == "linear" else None
+    r = _err(outs_b[1], ref) if ref is not None else {"max_abs": 0.0, "ref_max": 1.0}
+    # same plan, same K order: grouped == separate to the last bit (x 1000 so that one differing ulp fails)
+    return {"max_abs": worst * 1000 + r["max_abs"] + (0.0 if o2_ok else 1e3), "ref_max": r["ref_max"]}
 
 
 def case_grouped_linear():
