@@ -81,7 +81,7 @@ SYMBOLS = {
     "ea_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ea_small_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ea_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
-    "ea_out_cfg_ddim": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ea_out_cfg_ddim": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ea_step_gather": (_I, [_P, _I, _I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), _P]),
     "ea_sam_relpos": (_I, [_P, _L, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ea_window_partition": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

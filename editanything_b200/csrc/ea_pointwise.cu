@@ -363,7 +363,8 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
                                     float guidance, const float* __restrict__ known,
                                     const float* __restrict__ noise,
                                     const float* __restrict__ mask, ea_half* __restrict__ lat_half,
-                                    int* __restrict__ step_ctr, int Nimg, int H, int W, int C) {
+                                    int* __restrict__ step_ctr, float* __restrict__ hist, int Nimg, int H, int W,
+                                    int C) {
   pdl_launch_dependents();
   pdl_wait();
   // device-side step counter of the captured loop: the first kernel of the step (step_gather_kernel) read it,
@@ -429,6 +430,20 @@ __global__ void out_cfg_ddim_kernel(const ea_half* __restrict__ xn, const float*
       float xt = latents[gw * 4 + o];
       float x0 = (xt - s1a * e) / sa;       // :215
       float xp = sap * x0 + s1ap * e;       // :226-230 (eta = 0)
+      if (hist && coef[7] != 0.f) {
+        // Linear multistep predictor-corrector (UniPC, the scheduler every reference entry point installs:
+        // editany_lora.py:383,418) - all coefficients are functions of the timestep table, precomputed per step:
+        //   xc = kx x + kl last + k1 m1 + k2 m2 + k0 x0    (corrector; identity on the first step)
+        //   x' = px xc + p0 x0 + p1 m1                     (predictor for the next timestep)
+        //   m2 <- m1, m1 <- x0, last <- xc                 (history of x0 predictions / corrected samples)
+        const long long n4 = npix * 4, idx = gw * 4 + o;
+        const float m1 = hist[idx], m2 = hist[n4 + idx], last = hist[2 * n4 + idx];
+        const float xc = coef[8] * xt + coef[9] * last + coef[10] * m1 + coef[11] * m2 + coef[12] * x0;
+        xp = coef[13] * xc + coef[14] * x0 + coef[15] * m1;
+        hist[n4 + idx] = m1;
+        hist[idx] = x0;
+        hist[2 * n4 + idx] = xc;
+      }
       if (known) {
         // inpaint blend (utils/stable_diffusion_controlnet_inpaint.py:1647-1656).  With `noise` the kept
         // region is re-noised here: add_noise(init, noise, t_next) = coef[4] * init + coef[5] * noise, and
@@ -868,7 +883,7 @@ extern "C" int ea_timestep_embedding(const float* t, float* out, int B, int dim,
 extern "C" int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
                                float* eps_out, const float* coef, float guidance,
                                const float* known, const float* noise, const float* mask, void* lat_half_out,
-                               int* step_counter, int Nimg, int H, int W, int C, void* stream) {
+                               int* step_counter, float* hist, int Nimg, int H, int W, int C, void* stream) {
   if (!xn || !w || !bias || (!latents && !eps_out)) return EA_ERR_ARG;
   if (latents && !coef) return EA_ERR_ARG;
   if ((known && !mask) || (noise && !known)) return EA_ERR_ARG;
@@ -876,7 +891,7 @@ extern "C" int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias
   long long npix = (long long)Nimg * H * W;
   const int wpc = 4;
   ea_launch(out_cfg_ddim_kernel, dim3((unsigned)((npix + wpc - 1) / wpc)), dim3(wpc * 32), (size_t)(0), EA_STREAM(stream), reinterpret_cast<const ea_half*>(xn), w, bias, latents, eps_out, coef, guidance, known, noise, mask,
-      reinterpret_cast<ea_half*>(lat_half_out), step_counter, Nimg, H, W, C);
+      reinterpret_cast<ea_half*>(lat_half_out), step_counter, hist, Nimg, H, W, C);
   return EA_LAUNCH_OK();
 }
 

@@ -29,10 +29,12 @@ def ddim_schedule(num_steps, linear_start=0.00085, linear_end=0.012, T=1000):
 
 
 class DenoiseEngine:
-    def __init__(self, cfg: UNetConfig, unet_sd, controlnet_sds, device, backend=None):
+    def __init__(self, cfg: UNetConfig, unet_sd, controlnet_sds, device, backend=None, unet_packed=None):
+        """unet_packed: an already packed UNet (another engine's `.unet`) to share instead of packing `unet_sd`
+        again - the reference's tile pipeline runs the same base model as the main one (editany_lora.py:395-405)."""
         self.cfg, self.dev = cfg, device
         self.ops = backend or _cuda_ops
-        self.unet = PackedNet(cfg, "unet", unet_sd, device, backend)
+        self.unet = unet_packed if unet_packed is not None else PackedNet(cfg, "unet", unet_sd, device, backend)
         self.cns = [PackedNet(cfg, "controlnet", sd, device, backend) for sd in controlnet_sds]
         self.runner = UNetRunner(self.unet, self.cns, device)
         self.hdt = self.unet.hdt
@@ -100,7 +102,7 @@ class DenoiseEngine:
             nets = [self.unet] + self.cns
             self.emb_bufs = [torch.zeros(self.B, n.emb_total, device=self.dev, dtype=torch.float32) for n in nets]
             self.t_dev = torch.zeros(self.B, device=self.dev, dtype=torch.float32)
-            self.coef_dev = torch.zeros(8, device=self.dev, dtype=torch.float32)
+            self.coef_dev = torch.zeros(16, device=self.dev, dtype=torch.float32)
             self.step_ctr = torch.zeros(1, device=self.dev, dtype=torch.int32)
             self.gn_ws = torch.zeros(self.B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
             self._sched_key, self._sched_cap, self.n_steps = None, 0, 0
@@ -124,7 +126,7 @@ class DenoiseEngine:
             buf.copy_(r)
 
     # -- the sampling schedule as device tables -------------------------------------------------
-    def set_schedule(self, timesteps, alphas, alphas_prev, blend=None):
+    def set_schedule(self, timesteps, alphas, alphas_prev, blend=None, multistep=None):
         """Everything that changes from step to step of the loop (utils/...inpaint.py:1540-1656), as device
         tables with one row per step: the DDIM coefficients (cldm/ddim_hacked.py:203-231), the per-ResBlock
         time-embedding rows of every net, and the inpaint-blend terms.  `blend` = (k_init[S], k_noise[S],
@@ -137,13 +139,19 @@ class DenoiseEngine:
         if blend is None:
             blend = ([1.0] * S, [0.0] * S, [1.0] * S)
         rows = [[math.sqrt(a), math.sqrt(1.0 - a), math.sqrt(ap), math.sqrt(1.0 - ap), float(ki), float(kn), float(on), 0.0]
-                for a, ap, ki, kn, on in zip(alphas, alphas_prev, *blend)]
+                + [0.0] * 8 for a, ap, ki, kn, on in zip(alphas, alphas_prev, *blend)]
+        if multistep is not None:
+            # linear multistep predictor-corrector (UniPC): per-step coefficient rows of
+            # schedulers.UniPCMultistepScheduler.coefficient_rows(); mode flag coef[7] = 1
+            for r, m in zip(rows, multistep):
+                r[0], r[1], r[7] = m["alpha"], m["sigma"], 1.0
+                r[8:16] = [m["kx"], m["kl"], m["k1"], m["k2"], m["k0"], m["px"], m["p0"], m["p1"]]
         key = (tuple(ts), tuple(map(tuple, rows)), self.B)
         if key == self._sched_key:
             return
         if S > self._sched_cap:
             cap = ((S + 63) // 64) * 64
-            self.coef_tab = torch.zeros(cap, 8, device=self.dev, dtype=torch.float32)
+            self.coef_tab = torch.zeros(cap, 16, device=self.dev, dtype=torch.float32)
             self.emb_tabs = [torch.zeros(cap, *b.shape, device=self.dev, dtype=torch.float32) for b in self.emb_bufs]
             self._sched_cap = cap
             self._graph = None        # table addresses are baked into the captured step
@@ -177,7 +185,7 @@ class DenoiseEngine:
                                       embs=self.emb_bufs, ctx_ls=self.ctx_ls)
         self.ops.out_cfg_ddim(xn, self.unet.w["out.w"], self.unet.w["out.cb"], latents=self.lat,
                               coef=self.coef_dev, guidance=self.guidance, known=self.known, noise=self.noise,
-                              mask=self.mask, lat_half_out=self.x_half, step_counter=self.step_ctr,
+                              mask=self.mask, lat_half_out=self.x_half, step_counter=self.step_ctr, hist=self.hist,
                               Nimg=self.B // 2, H=H, W=W_, C_=self.cfg.model_channels)
 
     def begin(self, latents_nchw, guidance, known_nchw=None, mask_n1hw=None, noise_nchw=None, use_graph=True):
@@ -201,6 +209,8 @@ class DenoiseEngine:
         else:
             m = zeros[..., 0].contiguous()
         self._keep("mask", m)
+        # history of the multistep schedulers (x0 predictions of the two previous steps, previous corrected sample)
+        self._keep("hist", torch.zeros((3,) + tuple(lat.shape), device=self.dev, dtype=torch.float32))
         use = use_graph and self.ops is _cuda_ops
         if use != getattr(self, "_use_graph", None):
             self._graph = None

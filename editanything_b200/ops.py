@@ -233,11 +233,11 @@ def timestep_embedding(t, out, *, B, dim):
 
 
 def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, noise=None,
-                 mask=None, lat_half_out=None, step_counter=None, Nimg, H, W, C_):
+                 mask=None, lat_half_out=None, step_counter=None, hist=None, Nimg, H, W, C_):
     lib = L.lib()
     L.check(lib.ea_out_cfg_ddim(_p(xn), _p(w), _p(bias), _p(latents), _p(eps_out), _p(coef),
                                 float(guidance), _p(known), _p(noise), _p(mask), _p(lat_half_out),
-                                _p(step_counter), Nimg, H, W, C_, _stream()), "ea_out_cfg_ddim")
+                                _p(step_counter), _p(hist), Nimg, H, W, C_, _stream()), "ea_out_cfg_ddim")
 
 
 def step_gather(step_counter, n_rows, tables, dsts):

@@ -22,6 +22,8 @@ import torch
 import torch.nn.functional as F
 
 from .denoise import DenoiseEngine, ddim_schedule
+from .loading import ControlNetModel, ControlNetModel2  # noqa: F401  (the names editany_lora.py imports)
+from .schedulers import UniPCMultistepScheduler
 
 try:  # PIL is only needed for PIL inputs / output_type="pil"
     import PIL.Image
@@ -44,8 +46,8 @@ class DDIMScheduler:
     init_noise_sigma = 1.0
 
     def __init__(self, linear_start=0.00085, linear_end=0.012, num_train_timesteps=1000):
-        self.config = SimpleNamespace(beta_start=linear_start, beta_end=linear_end,
-                                      num_train_timesteps=num_train_timesteps)
+        self.config = SimpleNamespace(beta_start=linear_start, beta_end=linear_end, beta_schedule="scaled_linear",
+                                      num_train_timesteps=num_train_timesteps, prediction_type="epsilon")
         betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, num_train_timesteps, dtype=np.float64) ** 2
         self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         self.timesteps = None
@@ -166,6 +168,41 @@ class StableDiffusionControlNetInpaintPipeline:
         self.unet = _NetStub(engine.cfg.in_channels, dt)
         self.controlnet = _NetStub(engine.cfg.in_channels, dt, nets=[_NetStub(4, dt) for _ in engine.cns])
         self.vae_scale_factor = 8 if vae is None else 2 ** (len(vae.config.block_out_channels) - 1)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, controlnet=None, torch_dtype=None, safety_checker=None,
+                        feature_extractor=None, device=None, share_with=None, text_encoder=None, tokenizer=None,
+                        vae=None, scheduler=None, **_unused):
+        """editany_lora.py:372-377: `from_pretrained(base_model_path, controlnet=[...], torch_dtype=torch.float16,
+        safety_checker=None)`.  `controlnet`: one `ControlNetModel(2)` or a list (editanything_b200.loading);
+        components may be passed in like diffusers allows (text_encoder=, tokenizer=, vae=, scheduler=).
+        `share_with`: another pipeline of the same base model whose packed UNet, VAE, text encoder and tokenizer
+        are reused (the tile-refinement pipeline, editany_lora.py:391-423)."""
+        from .loading import load_pipeline_parts
+        dev = torch.device(device) if device is not None else torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        cns = [] if controlnet is None else (list(controlnet) if isinstance(controlnet, (list, tuple)) else [controlnet])
+        shared = share_with.engine.unet if share_with is not None else None
+        if share_with is not None:
+            text_encoder = text_encoder or share_with.text_encoder
+            tokenizer = tokenizer or share_with.tokenizer
+            vae = vae or share_with.vae
+        ucfg, usd, vae, text_encoder, tokenizer, sched = load_pipeline_parts(
+            pretrained_model_name_or_path, dev, text_encoder=text_encoder, tokenizer=tokenizer, vae=vae,
+            scheduler=scheduler, unet_packed=shared)
+        for c in cns:
+            if c.cfg != ucfg:
+                raise ValueError(f"ControlNet topology {c.cfg} does not match the UNet {ucfg}")
+        eng = DenoiseEngine(ucfg, usd, [c.state_dict_ldm for c in cns], dev, unet_packed=shared)
+        pipe = cls(eng, vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, scheduler=sched,
+                   safety_checker=safety_checker, feature_extractor=feature_extractor)
+        for stub, c in zip(pipe.controlnet.nets, cns):
+            stub.config = c.config
+        return pipe
+
+    def load_textual_inversion(self, *a, **k):
+        """editany_lora.py:734 calls this inside a try / except that tolerates failure; textual-inversion tokens need
+        the diffusers loader mixin, which this backend does not carry."""
+        raise NotImplementedError("textual inversion embeddings are not supported by this backend")
 
     # the reference toggles these; they are no-ops on this backend (nothing to offload or swap)
     def enable_xformers_memory_efficient_attention(self, *a, **k):
@@ -418,7 +455,10 @@ class StableDiffusionControlNetInpaintPipeline:
         eng = self.engine
         dev = eng.dev
         eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale)
-        fused = isinstance(self.scheduler, DDIMScheduler)
+        # fused step: the built-in DDIM, and UniPC (what every reference entry point installs, editany_lora.py:383,418)
+        # through its per-step coefficient rows; any other scheduler object runs eng.eps + scheduler.step
+        unipc = isinstance(self.scheduler, UniPCMultistepScheduler) and self.scheduler.config.solver_order <= 2
+        fused = isinstance(self.scheduler, DDIMScheduler) or unipc
         n_t = len(timesteps)
         blend_steps = 0 if alignment_ratio is None else sum(1 for i in range(n_t) if i < n_t * alignment_ratio)
         if blend_steps and blend_steps >= n_t:
@@ -430,7 +470,8 @@ class StableDiffusionControlNetInpaintPipeline:
         noise_d, init_d, m_d = noise.to(dev, torch.float32), init_lat.to(dev, torch.float32), m.to(dev, torch.float32)
         if fused:
             acp = self.scheduler.alphas_cumprod
-            coefs = [self.scheduler.coefficients(t) for t in timesteps]
+            coefs = [(float(acp[int(t)]), float(acp[int(t)])) for t in timesteps] if unipc else \
+                [self.scheduler.coefficients(t) for t in timesteps]
             # the kept region of step i is add_noise(init, noise, timesteps[i + 1]) while i < len * alignment_ratio
             # (:1647-1656).  With a callback the blend runs on the host side AFTER the callback, like the reference
             # (:1640-1656 calls back with the un-blended latents); otherwise it is fused into the step's last kernel.
@@ -439,7 +480,8 @@ class StableDiffusionControlNetInpaintPipeline:
                       if i < blend_steps else (1.0, 0.0) for i in range(n_t)]
             on = [1.0 if (i < blend_steps and not host_blend) else 0.0 for i in range(n_t)]
             eng.set_schedule([int(t) for t in timesteps], [c[0] for c in coefs], [c[1] for c in coefs],
-                             blend=([k[0] for k in k_next], [k[1] for k in k_next], on))
+                             blend=([k[0] for k in k_next], [k[1] for k in k_next], on),
+                             multistep=self.scheduler.coefficient_rows() if unipc else None)
             eng.begin(lat, guidance_scale, known_nchw=init_d if blend_steps else None,
                       mask_n1hw=m_d if blend_steps else None, noise_nchw=noise_d if blend_steps else None)
             for i, t in enumerate(timesteps):

@@ -224,7 +224,13 @@ int ea_timestep_embedding(const float* t, float* out, int B, int dim, void* stre
  * xn: NHWC half [2*Nimg, H, W, C] (first Nimg = unconditional, last Nimg = conditional);
  * w: fp32 [4, 3, 3, C]; bias fp32 [4]; latents fp32 NHWC [Nimg, H, W, 4] updated in place;
  * eps_out (optional) fp32 [2*Nimg, H, W, 4] raw network output;
- * coef: device fp32 [8] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev), k_init, k_noise, blend_on, 0};
+ * coef: device fp32 [16] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev), k_init, k_noise, blend_on, mode,
+ *   kx, kl, k1, k2, k0, px, p0, p1}.  mode 0: the DDIM update above.  mode 1 (with `hist`): a linear multistep
+ *   predictor-corrector step - UniPCMultistepScheduler, the scheduler the reference installs on every pipeline
+ *   (editany_lora.py:383,418): x0 = (x - coef[1] eps) / coef[0]; xc = kx x + kl last + k1 m1 + k2 m2 + k0 x0;
+ *   x' = px xc + p0 x0 + p1 m1; then m2 <- m1, m1 <- x0, last <- xc, with hist = fp32 [3][Nimg,H,W,4] = {m1, m2, last}
+ *   (the x0 predictions of the two previous steps and the previous corrected sample).  The coefficients depend on
+ *   the timestep table only (editanything_b200/schedulers.py:coefficient_rows).
  * blend (optional): known fp32 NHWC [Nimg,H,W,4], mask fp32 [Nimg,H,W] (1 = keep known).  With `noise`
  *   (optional, fp32 like known) the kept region is add_noise(known, noise, t_next) = k_init * known +
  *   k_noise * noise (utils/stable_diffusion_controlnet_inpaint.py:1650-1656) and blend_on (0 / 1) gates the
@@ -235,7 +241,7 @@ int ea_timestep_embedding(const float* t, float* out, int B, int dim, void* stre
 int ea_out_cfg_ddim(const void* xn, const float* w, const float* bias, float* latents,
                     float* eps_out, const float* coef, float guidance, const float* known,
                     const float* noise, const float* mask, void* lat_half_out, int* step_counter,
-                    int Nimg, int H, int W, int C, void* stream);
+                    float* hist, int Nimg, int H, int W, int C, void* stream);
 
 /* ---- ea_step_gather: first kernel of a captured denoising step ---------------------------------
  * The loop of utils/stable_diffusion_controlnet_inpaint.py:1540-1656 changes only scalars from step to step

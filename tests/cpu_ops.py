@@ -194,7 +194,7 @@ def step_gather(step_counter, n_rows, tables, dsts):
 
 
 def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance=1.0, known=None, noise=None,
-                 mask=None, lat_half_out=None, step_counter=None, Nimg, H, W, C_):
+                 mask=None, lat_half_out=None, step_counter=None, hist=None, Nimg, H, W, C_):
     _bump()
     eps = F.conv2d(xn.float().permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
     if eps_out is not None:
@@ -204,6 +204,14 @@ def out_cfg_ddim(xn, w, bias, *, latents=None, eps_out=None, coef=None, guidance
         sa, s1a, sap, s1ap = [float(c) for c in coef[:4]]
         x0 = (latents - s1a * e) / sa
         xp = sap * x0 + s1ap * e
+        if hist is not None and float(coef[7]) != 0.0:
+            c = [float(v) for v in coef]
+            m1, m2, last = hist[0].clone(), hist[1].clone(), hist[2].clone()
+            xc = c[8] * latents + c[9] * last + c[10] * m1 + c[11] * m2 + c[12] * x0
+            xp = c[13] * xc + c[14] * x0 + c[15] * m1
+            hist[1].copy_(m1)
+            hist[0].copy_(x0)
+            hist[2].copy_(xc)
         if known is not None:
             kn, mk = known, mask[..., None]
             if noise is not None:

@@ -248,3 +248,40 @@ def test_callback_sees_unblended_latents():
     assert (a - ref).abs().max().item() < 2e-4 and (b - ref).abs().max().item() < 2e-4
     # step 0's callback latents differ from the blended ones inside the kept region
     assert (seen[0] - a).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("alignment_ratio", [None, 0.5])
+def test_unipc_fused_update_matches_scheduler_object_loop(alignment_ratio):
+    """`pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config)` (editany_lora.py:383): the fused
+    device-side multistep update (coefficient rows + history buffers) == the reference loop re-enacted with the
+    scheduler OBJECT's step() on the oracle networks."""
+    from editanything_b200.schedulers import UniPCMultistepScheduler
+    cfg, usd, csds, pipe, image, mask, conds, pe, ne = _setup()
+    pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config)
+    steps, gs = 6, 7.0
+    out = pipe(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=64, width=64,
+               num_inference_steps=steps, guidance_scale=gs, generator=torch.manual_seed(7), prompt_embeds=pe,
+               negative_prompt_embeds=ne, output_type="latent", controlnet_conditioning_scale=[0.5, 1.0],
+               alignment_ratio=alignment_ratio, num_images_per_prompt=1).images
+    # re-enactment with the scheduler object
+    vae = FakeVAE()
+    sch = UniPCMultistepScheduler.from_config(DDIMScheduler().config)
+    sch.set_timesteps(steps)
+    ts = sch.timesteps
+    ctx = torch.cat([ne, pe])
+    hints = [torch.cat([c] * 2) for c in conds]
+    lat = torch.randn((1, 4, 8, 8), generator=torch.Generator().manual_seed(7))
+    noise = lat
+    init = 0.18215 * vae.encode(image).latent_dist.sample()
+    m = 1 - F.interpolate((mask >= 0.5).float(), (8, 8), mode="nearest")
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    for i, t in enumerate(ts):
+        with torch.no_grad():
+            e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], torch.cat([lat] * 2), torch.full((2,), int(t)), ctx, hints,
+                              [0.5, 1.0])
+        lat = sch.step(e[:1] + gs * (e[1:] - e[:1]), t, lat).prev_sample
+        if alignment_ratio is not None and i < len(ts) * alignment_ratio:
+            lat = sch.add_noise(init, noise, ts[i + 1]) * m + lat * (1 - m)
+    if alignment_ratio is None:
+        lat = init * m + lat * (1 - m)
+    assert (out - lat).abs().max().item() < 5e-4, (out - lat).abs().max().item()
