@@ -94,7 +94,7 @@ def _gemm_traffic():
         doc = json.load(open(path))
         n = rd = 0
         for k, v in doc["kernels"].items():
-            if "ea_gemm_kernel" in k:
+            if "ea_gemm" in k:
                 n += v["launches"]
                 rd += v["dram_bytes_per_launch"] * v["launches"]
         if n:

@@ -1,0 +1,14 @@
+"""The operator table the engines run on: `editanything_b200.ops` (ctypes over libea_b200.so, sm_100a kernels).
+
+There is ONE product backend and no fallback.  `OPS` exists so that the host-side logic (graph of launches, buffer
+plumbing, scheduling, checkpoint loading) can be exercised on machines without a GPU: the CPU test-suite assigns
+`tests/cpu_ops.py` - a torch emulation of each operator's contract, test infrastructure only - here or passes it as
+`backend=`.  Nothing in the package ever sets it."""
+OPS = None
+
+
+def default_ops():
+    if OPS is not None:
+        return OPS
+    from . import ops
+    return ops

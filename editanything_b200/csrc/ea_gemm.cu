@@ -74,6 +74,7 @@ struct GemmKParams {
   const float* ln_g;        // [N]
   int ln_parts;
   float ln_inv_c, ln_eps;
+  const float* row_scale;   // [M] fp32 per-row output factor (general / split-K epilogues only) or null
   int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
@@ -143,6 +144,29 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// LayerNorm fold, consumer side: one row's mean / rstd from the producer's per-32-column partial (sum, sumsq) pairs.
+// The loads of a batch of 16 partials are all issued before the first add - a plain loop compiled to one dependent L2
+// round trip per partial (10 for C = 320, 40 for C = 1280: 22 % of all stall samples of the GEGLU launch,
+// profiles/r02c_gemm_ncu_source_hot.txt).  The adds keep their fixed order, so the result stays deterministic.
+__device__ __forceinline__ void ln_row_stats(const GemmKParams& p, long long m, float& ln_r, float& ln_nm) {
+  float s = 0.f, q = 0.f;
+  const float2* base = p.ln_stats + m;
+  for (int j0 = 0; j0 < p.ln_parts; j0 += 16) {
+    float2 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      v[u] = (j0 + u < p.ln_parts) ? __ldcg(base + (size_t)(j0 + u) * p.M) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      s += v[u].x;
+      q += v[u].y;
+    }
+  }
+  const float mu = s * p.ln_inv_c;
+  ln_r = rsqrtf(fmaxf(q * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
+  ln_nm = -ln_r * mu;
 }
 
 // Out-of-line activation for the rarely taken paths (general / split-K epilogues, SiLU): one copy of
@@ -295,6 +319,11 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmKParams& p, const Row
   if (p.out_scale != 1.0f) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= p.out_scale;
+  }
+  if (p.row_scale) {   // spatial conditioning-scale map (utils/stable_diffusion_controlnet.py:789-802): one factor per row
+    const float rs = __ldg(p.row_scale + m);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= rs;
   }
   if (p.residual) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n_first);
@@ -599,7 +628,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
     // per-chunk work is TMEM load -> FMA -> 16-byte stores with the NEXT chunk's residual already in
     // flight (before: four dependent global round trips per 32-column chunk, ~5400 clk per tile).
     const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
-    const bool fast = p.splits == 1 && !geglu && !p.out_f32 && !p.accumulate && (b_last - b_first) <= 1;
+    const bool fast = p.splits == 1 && !geglu && !p.out_f32 && !p.accumulate && !p.row_scale && (b_last - b_first) <= 1;
     uint4 rres[8];   // next 64-column group of the residual (coalesced layout)
     const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
     const bool has_res = p.residual != nullptr;
@@ -607,17 +636,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
     // summation order: deterministic), while the main loop runs.  out = acc * ln_r + ln_nm * g[n] + c[n].
     const bool ln = p.ln_stats != nullptr;
     float ln_r = 1.f, ln_nm = 0.f;
-    if (ln && ri.ok) {
-      float s = 0.f, q = 0.f;
-      for (int j = 0; j < p.ln_parts; ++j) {
-        const float2 v = __ldcg(p.ln_stats + (size_t)j * p.M + ri.m);
-        s += v.x;
-        q += v.y;
-      }
-      const float mu = s * p.ln_inv_c;
-      ln_r = rsqrtf(fmaxf(q * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
-      ln_nm = -ln_r * mu;
-    }
+    if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
     if (fast) {
       for (int i = et; i < p.BN; i += 128) {
         const int col = ncol0 + i;
@@ -1150,17 +1169,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       // LayerNorm fold, consumer side (see ea_gemm_kernel)
       const bool ln = p.ln_stats != nullptr;
       float ln_r = 1.f, ln_nm = 0.f;
-      if (ln && ri.ok) {
-        float s = 0.f, q = 0.f;
-        for (int j = 0; j < p.ln_parts; ++j) {
-          const float2 v = __ldcg(p.ln_stats + (size_t)j * p.M + ri.m);
-          s += v.x;
-          q += v.y;
-        }
-        const float mu = s * p.ln_inv_c;
-        ln_r = rsqrtf(fmaxf(q * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
-        ln_nm = -ln_r * mu;
-      }
+      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
       if (!geglu) {
         for (int i = et; i < p.BN; i += EPI_THREADS) {
           const int col = ncol0 + i;
@@ -1542,6 +1551,8 @@ static int gemm_fill_group(const ea_gemm_args* a, GemmGroup& G, GemmShape& sh) {
   p.act = a->act;
   p.out_scale = a->out_scale;
   p.accumulate = a->accumulate;
+  p.row_scale = a->row_scale;
+  if (a->row_scale && (a->act == EA_ACT_GEGLU || a->rowstats_out || a->ln_stats)) return EA_ERR_ARG;
   sh.ln_any = a->rowstats_out || a->ln_stats;
   if (sh.ln_any) {
     if (a->mode != EA_GEMM_LINEAR || a->rowvec || a->out_f32 || a->accumulate) return EA_ERR_ARG;
@@ -1622,6 +1633,7 @@ static bool gemm_same_problem(const ea_gemm_args* a, const ea_gemm_args* b) {
   return a->mode == b->mode && a->M == b->M && a->N == b->N && a->K == b->K && a->Bsz == b->Bsz && a->H == b->H &&
          a->W == b->W && a->Cin == b->Cin && a->Cin_extra == b->Cin_extra && (!a->a_extra) == (!b->a_extra) &&
          a->act == b->act && a->accumulate == b->accumulate && (!a->out_f32) == (!b->out_f32) &&
+         (!a->row_scale) == (!b->row_scale) &&
          (!a->rowvec) == (!b->rowvec) && a->rows_per_batch == b->rows_per_batch &&
          (!a->rowstats_out) == (!b->rowstats_out) && (!a->ln_stats) == (!b->ln_stats) && a->ln_parts == b->ln_parts &&
          a->force_bn == b->force_bn && a->force_stages == b->force_stages && a->force_splits == b->force_splits &&
@@ -1666,7 +1678,7 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
       !a->rowvec || (a->mode == EA_GEMM_LINEAR
                          ? (a->rows_per_batch == 0 || a->rows_per_batch >= BM || a->rows_per_batch == BM / 2)
                          : p0.bn <= 2);      // a tile may span at most two batch elements (fast epilogue)
-  const bool persist_ok = !a->out_f32 && !a->accumulate && a->force_splits <= 1 && a->force_2cta <= 0 &&
+  const bool persist_ok = !a->out_f32 && !a->accumulate && !a->row_scale && a->force_splits <= 1 && a->force_2cta <= 0 &&
                           (a->act == EA_ACT_GEGLU || batch_ok);
   bool persist = persist_ok && (a->force_persistent > 0 || (a->force_persistent == 0 && persist_env > 0));
   const int persist_wg = (a->force_persistent == 2 || (a->force_persistent == 0 && persist_env >= 2)) ? 2 : 1;

@@ -698,10 +698,11 @@ __global__ void image_out_kernel(const ea_half* __restrict__ x, long long ldx, f
 // the tensor-core path; the whole filter bank lives in shared memory, a thread owns one pixel and 8
 // consecutive output channels (16-byte stores), the 9*Cin input taps sit in registers.
 template <int CIN>
-__global__ void conv_smallcin_kernel(const ea_half* __restrict__ x, const float* __restrict__ w,
-                                     const float* __restrict__ bias, ea_half* __restrict__ out,
-                                     long long ldo, ea_half* __restrict__ out2, long long ldo2,
-                                     const ea_half* __restrict__ add, int B, int H, int W, int Cout) {
+__global__ void __launch_bounds__(256)
+conv_smallcin_kernel(const ea_half* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ bias, ea_half* __restrict__ out,
+                     long long ldo, ea_half* __restrict__ out2, long long ldo2,
+                     const ea_half* __restrict__ add, int B, int H, int W, int Cout) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float wsm[];  // [9*CIN][Cout] + bias[Cout]
@@ -713,46 +714,71 @@ __global__ void conv_smallcin_kernel(const ea_half* __restrict__ x, const float*
   }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[nw + i] = bias ? bias[i] : 0.f;
   __syncthreads();
+  // A thread owns 8 consecutive output channels of PX = 4 horizontally adjacent pixels: every weight read from
+  // shared memory feeds 4 FMAs (one pixel per thread made the kernel shared-memory-bandwidth bound: 72 us for the
+  // 94 MFLOP of conv_in at 64x64, profiles/r02c_launches_summary.txt), and a persistent grid loads the 46 KB filter
+  // bank once per CTA instead of once per 256 outputs.
+  constexpr int PX = 4;
   const int ngrp = Cout >> 3;
-  const long long total = (long long)B * H * W * ngrp;
+  const int wq_n = (W + PX - 1) / PX;
+  const long long total = (long long)B * H * wq_n * ngrp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % ngrp);
-    const long long pix = idx / ngrp;
-    const int wo = (int)(pix % W);
-    const int ho = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    float acc[8];
+    const long long q = idx / ngrp;
+    const int wo0 = (int)(q % wq_n) * PX;
+    const int ho = (int)((q / wq_n) % H);
+    const int b = (int)(q / ((long long)wq_n * H));
+    float acc[PX][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = wsm[nw + g * 8 + j];
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = wsm[nw + g * 8 + j];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho + kh - 1;
       if (hi < 0 || hi >= H) continue;
+      float xin[PX + 2][CIN];          // input columns wo0 - 1 .. wo0 + PX of row hi (zero outside the image)
+#pragma unroll
+      for (int cidx = 0; cidx < PX + 2; ++cidx) {
+        const int wi = wo0 + cidx - 1;
+        const bool ok = wi >= 0 && wi < W;
+        const ea_half* xp = x + (((long long)b * H + hi) * W + (ok ? wi : 0)) * CIN;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xin[cidx][c] = ok ? ea_h2f(xp[c]) : 0.f;
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo + kw - 1;
-        if (wi < 0 || wi >= W) continue;
-        const ea_half* xp = x + (((long long)b * H + hi) * W + wi) * CIN;
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
-          const float xv = ea_h2f(xp[c]);
-          const float* wr = wsm + ((kh * 3 + kw) * CIN + c) * Cout + g * 8;
+          const float4* wr = reinterpret_cast<const float4*>(wsm + ((kh * 3 + kw) * CIN + c) * Cout + g * 8);
+          const float4 w0 = wr[0], w1 = wr[1];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+          for (int p = 0; p < PX; ++p) {
+            const float xv = xin[p + kw][c];
+            acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+            acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+            acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+            acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
+          }
         }
       }
     }
-    if (add) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(add + pix * Cout + g * 8));
-      float2 a0 = ea_unpack2(u.x), a1 = ea_unpack2(u.y), a2 = ea_unpack2(u.z), a3 = ea_unpack2(u.w);
-      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
-      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (wo0 + p >= W) break;
+      const long long pix = ((long long)b * H + ho) * W + wo0 + p;
+      if (add) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(add + pix * Cout + g * 8));
+        float2 a0 = ea_unpack2(u.x), a1 = ea_unpack2(u.y), a2 = ea_unpack2(u.z), a3 = ea_unpack2(u.w);
+        acc[p][0] += a0.x; acc[p][1] += a0.y; acc[p][2] += a1.x; acc[p][3] += a1.y;
+        acc[p][4] += a2.x; acc[p][5] += a2.y; acc[p][6] += a3.x; acc[p][7] += a3.y;
+      }
+      const uint4 o = make_uint4(ea_pack2(acc[p][0], acc[p][1]), ea_pack2(acc[p][2], acc[p][3]),
+                                 ea_pack2(acc[p][4], acc[p][5]), ea_pack2(acc[p][6], acc[p][7]));
+      *reinterpret_cast<uint4*>(out + pix * ldo + g * 8) = o;
+      if (out2) *reinterpret_cast<uint4*>(out2 + pix * ldo2 + g * 8) = o;
     }
-    const uint4 o = make_uint4(ea_pack2(acc[0], acc[1]), ea_pack2(acc[2], acc[3]),
-                               ea_pack2(acc[4], acc[5]), ea_pack2(acc[6], acc[7]));
-    *reinterpret_cast<uint4*>(out + pix * ldo + g * 8) = o;
-    if (out2) *reinterpret_cast<uint4*>(out2 + pix * ldo2 + g * 8) = o;
   }
 }
 
@@ -997,9 +1023,9 @@ extern "C" int ea_conv_in(const void* x, const float* w, const float* bias, void
   if (Cout % 8 != 0 || (Cin != 4 && Cin != 8) || ldo % 8 != 0 || (out2 && ldo2 % 8 != 0))
     return EA_ERR_SHAPE;
   const int smem = (9 * Cin * Cout + Cout) * (int)sizeof(float);
-  const long long total = (long long)B * H * W * (Cout / 8);
+  const long long total = (long long)B * H * ((W + 3) / 4) * (Cout / 8);   // a thread = 4 pixels x 8 channels
   int grid = (int)((total + 255) / 256);
-  if (grid > 148) grid = 148;   // the 46 KB filter bank is loaded once per CTA: one CTA per SM
+  if (grid > 296) grid = 296;   // the filter bank (46 KB for 4 -> 320) is loaded once per CTA: two CTAs per SM
   if (grid < 1) grid = 1;
   cudaStream_t st = EA_STREAM(stream);
   const ea_half* xx = reinterpret_cast<const ea_half*>(x);

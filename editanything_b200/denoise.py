@@ -10,7 +10,7 @@ import math
 import numpy as np
 import torch
 
-from . import ops as _cuda_ops
+from ._backend import default_ops
 from .nets import PackedNet, UNetRunner
 from .unet_spec import UNetConfig
 
@@ -33,7 +33,7 @@ class DenoiseEngine:
         """unet_packed: an already packed UNet (another engine's `.unet`) to share instead of packing `unet_sd`
         again - the reference's tile pipeline runs the same base model as the main one (editany_lora.py:395-405)."""
         self.cfg, self.dev = cfg, device
-        self.ops = backend or _cuda_ops
+        self.ops = backend or default_ops()
         self.unet = unet_packed if unet_packed is not None else PackedNet(cfg, "unet", unet_sd, device, backend)
         self.cns = [PackedNet(cfg, "controlnet", sd, device, backend) for sd in controlnet_sds]
         self.runner = UNetRunner(self.unet, self.cns, device)
@@ -56,7 +56,31 @@ class DenoiseEngine:
         setattr(self, name, new)
         return new
 
-    def prepare(self, ctx, hints, scales):
+    def _norm_scale(self, s, guess_mode, B, lat_hw):
+        """One net's conditioning scale in the form nets.UNetRunner.zc_scale reads: a plain float, or - for guess mode
+        / a spatial map (ControlNetModel2.forward, utils/stable_diffusion_controlnet.py:777-802) - a dict with the 13
+        logspace(-1, 0, 13) per-residual factors and / or the map resized (bilinear, align_corners=True) to every
+        residual resolution, flattened to one factor per output row [B * h * w]."""
+        if not guess_mode and not torch.is_tensor(s):
+            return float(s)
+        out = {"base": 1.0 if torch.is_tensor(s) else float(s), "per_res": None, "maps": None}
+        if guess_mode:
+            if torch.is_tensor(s):
+                raise NotImplementedError("guess_mode with a spatial conditioning_scale map")
+            out["per_res"] = [float(v) for v in torch.logspace(-1, 0, len(self.unet.topo.input_chans) + 1)]
+        if torch.is_tensor(s):
+            m = s.to(self.dev, torch.float32)
+            m = m[None, None] if m.dim() == 2 else m[None] if m.dim() == 3 else m
+            maps = {}
+            h, w = lat_hw
+            for _ in range(len(self.cfg.channel_mult)):
+                r = torch.nn.functional.interpolate(m, (h, w), mode="bilinear", align_corners=True)
+                maps[(h, w)] = r.expand(B, 1, h, w).reshape(-1).contiguous()
+                h, w = h // 2, w // 2
+            out["maps"] = maps
+        return out
+
+    def prepare(self, ctx, hints, scales, guess_mode=False):
         """ctx: [B, L, D] prompt embeddings ([negative; positive] stacked for CFG,
         utils/stable_diffusion_controlnet_inpaint.py:1339-1347); hints: list of NCHW conditioning
         images [B, 3, 8h, 8w] (un-normalised, editany_lora.py:771-778,814-828); scales: list."""
@@ -93,9 +117,11 @@ class DenoiseEngine:
         else:
             self.hints = new_hints
             self._graph = None
-        new_scales = [float(s) for s in scales]
-        if getattr(self, "scales", None) != new_scales:
-            self._graph = None        # scales are baked into the zero-conv launches
+        lat_hw = (hints[0].shape[-2] // 8, hints[0].shape[-1] // 8) if len(hints) else (0, 0)
+        new_scales = [self._norm_scale(s, guess_mode, self.B, lat_hw) for s in scales]
+        plain = all(not isinstance(s, dict) for s in new_scales)
+        if not plain or getattr(self, "scales", None) != new_scales:
+            self._graph = None        # scales (and map addresses) are baked into the zero-conv launches
         self.scales = new_scales
         if not hasattr(self, "t_dev") or self.t_dev.shape[0] != self.B:
             self._emb_cache = {}
@@ -211,7 +237,7 @@ class DenoiseEngine:
         self._keep("mask", m)
         # history of the multistep schedulers (x0 predictions of the two previous steps, previous corrected sample)
         self._keep("hist", torch.zeros((3,) + tuple(lat.shape), device=self.dev, dtype=torch.float32))
-        use = use_graph and self.ops is _cuda_ops
+        use = use_graph and self.dev.type == "cuda"
         if use != getattr(self, "_use_graph", None):
             self._graph = None
         self._use_graph = use

@@ -20,7 +20,7 @@ import os
 import torch
 
 from . import _lib as L
-from . import ops as _cuda_ops
+from ._backend import default_ops
 from .unet_spec import HINT_STRIDES, UNetConfig, build_topology
 
 
@@ -44,7 +44,7 @@ class PackedNet:
 
     def __init__(self, cfg: UNetConfig, kind: str, state_dict, device, backend=None):
         self.cfg, self.kind = cfg, kind
-        self.ops = backend or _cuda_ops
+        self.ops = backend or default_ops()
         # LayerNorm folded into the GEMMs around it (ea_gemm_args.rowstats_out / ln_*): no LayerNorm launch, no
         # normalised tensor.  EA_LN_FOLD=0 keeps the separate ea_layernorm launches (A/B, debugging).
         self.ln_fold = os.environ.get("EA_LN_FOLD", "1") != "0"
@@ -435,12 +435,13 @@ class UNetRunner:
                 c = h.shape[-1]
                 M = h.shape[0] * h.shape[1] * h.shape[2]
                 p = f"zero_convs.{i}.0"
+                f, rs = self.zc_scale(scale, i, h.shape)
                 if deferred is not None:   # run after the concurrent streams have joined (shared slots)
-                    deferred.append((h.view(M, c), w[p + ".w"], slot, dict(M=M, bias=w[p + ".b"], out_scale=scale,
+                    deferred.append((h.view(M, c), w[p + ".w"], slot, dict(M=M, bias=w[p + ".b"], out_scale=f, row_scale=rs,
                                                                         accumulate=True, ldo=slot.stride(2))))
                 else:
-                    o.gemm(h.view(M, c), w[p + ".w"], slot, M=M, bias=w[p + ".b"], out_scale=scale, accumulate=True,
-                           ldo=slot.stride(2))
+                    o.gemm(h.view(M, c), w[p + ".w"], slot, M=M, bias=w[p + ".b"], out_scale=f, row_scale=rs,
+                           accumulate=True, ldo=slot.stride(2))
         mid_sink = sinks["mid"]
         if is_unet:
             h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws, final_out=mid_sink)
@@ -448,13 +449,30 @@ class UNetRunner:
             h = net._run_layers(topo.middle, h, emb_all, ctxc, gn_ws)
             c = h.shape[-1]
             M = h.shape[0] * h.shape[1] * h.shape[2]
+            f, rs = self.zc_scale(scale, None, h.shape)
             if deferred is not None:
-                deferred.append((h.view(M, c), w["mid_out.w"], mid_sink, dict(M=M, bias=w["mid_out.b"], out_scale=scale,
-                                                                             accumulate=True, ldo=mid_sink.stride(2))))
+                deferred.append((h.view(M, c), w["mid_out.w"], mid_sink, dict(M=M, bias=w["mid_out.b"], out_scale=f,
+                                                                             row_scale=rs, accumulate=True,
+                                                                             ldo=mid_sink.stride(2))))
             else:
-                o.gemm(h.view(M, c), w["mid_out.w"], mid_sink, M=M, bias=w["mid_out.b"], out_scale=scale,
+                o.gemm(h.view(M, c), w["mid_out.w"], mid_sink, M=M, bias=w["mid_out.b"], out_scale=f, row_scale=rs,
                        accumulate=True, ldo=mid_sink.stride(2))
         return h
+
+    @staticmethod
+    def zc_scale(scale, i, shape):
+        """(out_scale, row_scale) of zero-conv i (0..11 = down residuals, None = mid) for one net's conditioning
+        scale: a float, or the dict DenoiseEngine.prepare builds for guess mode (per-residual logspace factors) and
+        spatial maps (utils/stable_diffusion_controlnet.py:777-802)."""
+        if not isinstance(scale, dict):
+            return float(scale), None
+        f = scale["base"]
+        if scale.get("per_res") is not None:
+            f *= scale["per_res"][-1 if i is None else i]
+        rs = None
+        if scale.get("maps") is not None:
+            rs = scale["maps"][(shape[1], shape[2])]
+        return f, rs
 
     def precompute_context_lockstep(self, ctx):
         """Cross-attention K/V of the encoder + middle attention layers of every network, stacked along the batch
@@ -496,7 +514,8 @@ class UNetRunner:
             for k, cn in enumerate(self.cns):
                 pz = f"zero_convs.{i}.0" if i is not None else "mid_out"
                 wz, bz = (cn.w[pz + ".w"], cn.w[pz + ".b"])
-                o.gemm(h.chunk(n, 0)[1 + k].reshape(Mg, c), wz, slot, M=Mg, bias=bz, out_scale=float(scales[k]),
+                f, rs = self.zc_scale(scales[k], i, h.shape)
+                o.gemm(h.chunk(n, 0)[1 + k].reshape(Mg, c), wz, slot, M=Mg, bias=bz, out_scale=f, row_scale=rs,
                        accumulate=True, ldo=slot.stride(2))
 
         h = None
@@ -591,7 +610,7 @@ class UNetRunner:
                 with torch.cuda.stream(self._streams[k]):
                     o.set_lane(1 + k, True)
                     self._encoder(cn, x_half, embs[1 + k], ctx_cache[1 + k], lanes_ws[1 + k], guided_hint=hints[k],
-                                  sinks=sinks, scale=float(scales[k]), deferred=deferred)
+                                  sinks=sinks, scale=scales[k], deferred=deferred)
             for s in self._streams:
                 main.wait_stream(s)
             o.set_lane(0, False)
@@ -602,7 +621,7 @@ class UNetRunner:
             for k, cn in enumerate(self.cns):
                 emb_c = embs[1 + k]
                 self._encoder(cn, x_half, emb_c, ctx_cache[1 + k], gn_ws, guided_hint=hints[k], sinks=sinks,
-                              scale=float(scales[k]))
+                              scale=scales[k])
         topo = un.topo
         cats = sinks["cats"]
         h = None

@@ -61,7 +61,7 @@ def _fill_gemm(g, a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=No
                conv=None, a_extra=None, bias=None, rowvec=None, rows_per_batch=0, residual=None,
                out2=None, out_f32=None, act=L.EA_ACT_NONE, out_scale=1.0, accumulate=False,
                ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0, force_stages=0, force_splits=0, force_2cta=0,
-               force_persistent=0, rowstats_out=None, ln=None):
+               force_persistent=0, rowstats_out=None, ln=None, row_scale=None):
     """Fills one ea_gemm_args; returns the output tensor (allocated when the caller gave none)."""
     g.mode = mode
     g.N = N if N is not None else w.shape[0]
@@ -111,6 +111,8 @@ def _fill_gemm(g, a, w, out=None, *, mode=L.EA_GEMM_LINEAR, M=None, N=None, K=No
     g.force_2cta = force_2cta
     g.force_persistent = force_persistent
     g.no_spin = 1 if _CONCURRENT[0] else 0
+    if row_scale is not None:
+        g.row_scale = row_scale.data_ptr()
     if rowstats_out is not None:
         g.rowstats_out = rowstats_out.data_ptr()
     if ln is not None:

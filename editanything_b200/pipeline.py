@@ -409,8 +409,6 @@ class StableDiffusionControlNetInpaintPipeline:
                  reference_attn=True, reference_adain=True, ref_scale=1.0):
         if ref_image is not None:
             raise NotImplementedError("reference-only mode needs per-module hooks the fused UNet does not expose")
-        if guess_mode:
-            raise NotImplementedError("guess_mode (per-residual logspace scales) is not implemented")
         if eta != 0.0:
             raise NotImplementedError("only deterministic sampling (eta = 0) is fused")
         height, width = self._default_height_width(height, width, controlnet_conditioning_image)
@@ -454,7 +452,7 @@ class StableDiffusionControlNetInpaintPipeline:
 
         eng = self.engine
         dev = eng.dev
-        eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale)
+        eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale, guess_mode=guess_mode)
         # fused step: the built-in DDIM, and UniPC (what every reference entry point installs, editany_lora.py:383,418)
         # through its per-step coefficient rows; any other scheduler object runs eng.eps + scheduler.step
         unipc = isinstance(self.scheduler, UniPCMultistepScheduler) and self.scheduler.config.solver_order <= 2

@@ -22,7 +22,7 @@ Activations are channels-last half [tokens, C]; all accumulation fp32.
 import torch
 
 from . import _lib as L
-from . import ops as _cuda_ops
+from ._backend import default_ops
 from .sam_spec import SAM_TINY, SAM_VIT_H, SamEncoderConfig, make_sam_state_dict  # noqa: F401
 
 
@@ -37,7 +37,7 @@ def _gather_rel_pos(table, S):
 class SamEncoderEngine:
     def __init__(self, cfg: SamEncoderConfig, state_dict, device, backend=None):
         self.cfg, self.dev = cfg, device
-        self.ops = backend or _cuda_ops
+        self.ops = backend or default_ops()
         self.hdt = self.ops.half_dtype()
         sd = {k[len("image_encoder."):] if k.startswith("image_encoder.") else k: v for k, v in state_dict.items()}
         H, F = self._half, self._f32
@@ -151,7 +151,7 @@ class SamEncoderEngine:
         B = img.shape[0]
         if tuple(img.shape[1:]) != (cfg.in_chans, cfg.img_size, cfg.img_size):
             raise ValueError(f"expected [B,{cfg.in_chans},{cfg.img_size},{cfg.img_size}], got {tuple(img.shape)}")
-        if not use_graph or self.ops is not _cuda_ops:
+        if not use_graph or self.dev.type != "cuda":
             return self._encode_eager(img)
         st = self._graphs.get(B)
         if st is None:

@@ -26,7 +26,7 @@ import types
 import torch
 
 from . import _lib as L
-from . import ops as _cuda_ops
+from ._backend import default_ops
 from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, encoder_blocks, make_vae_state_dict  # noqa: F401
 
 
@@ -39,7 +39,7 @@ class _VaeBase:
 
     def _setup(self, cfg, device, backend):
         self.cfg, self.dev = cfg, device
-        self.ops = backend or _cuda_ops
+        self.ops = backend or default_ops()
         self.hdt = self.ops.half_dtype()
         self.config = types.SimpleNamespace(scaling_factor=cfg.scaling_factor, latent_channels=cfg.z_channels,
                                             block_out_channels=cfg.block_out_channels)
@@ -185,7 +185,7 @@ class VaeDecoderEngine(_VaeBase):
         """latents as the denoising loop leaves them -> fp32 [B, 3, 8h, 8w] in [0, 1]
         (decode_latents up to the .cpu().permute().numpy() plumbing).  On the CUDA backend the ~170
         launches are captured once per latent shape into a CUDA graph and replayed."""
-        if not use_graph or self.ops is not _cuda_ops:
+        if not use_graph or self.dev.type != "cuda":
             return self._decode(latents.float() / self.cfg.scaling_factor, post=True)
         return self._graphed(("dec",) + tuple(latents.shape), latents,
                              lambda x: self._decode(x / self.cfg.scaling_factor, post=True))
@@ -275,7 +275,7 @@ class VaeEncoderEngine(_VaeBase):
         f = 2 ** (self.cfg.num_resolutions - 1)
         if x.shape[2] % f or x.shape[3] % f:
             raise ValueError(f"image sides must be multiples of {f}")
-        if use_graph and self.ops is _cuda_ops:
+        if use_graph and self.dev.type == "cuda":
             m = self._graphed(("enc",) + tuple(x.shape), x, self._moments)
         else:
             m = self._moments(x.float())

@@ -125,6 +125,10 @@ typedef struct ea_gemm_args {
   const float* ln_g;         /* fp32 [N] */
   int ln_parts;
   float ln_eps;
+  const float* row_scale;    /* optional fp32 [M]: out row m is multiplied by row_scale[m] after act / out_scale and
+                                before residual / accumulate - the spatial `conditioning_scale` map of
+                                ControlNetModel2.forward (utils/stable_diffusion_controlnet.py:789-802), resized to
+                                the residual's resolution, as a factor of the zero-conv accumulation */
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K

@@ -33,7 +33,8 @@ def _bump(n=1):
 def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, conv=None, a_extra=None,
          bias=None, rowvec=None, rows_per_batch=0, residual=None, out2=None, out_f32=None, act=0,
          out_scale=1.0, accumulate=False, ldo=None, ldr=None, ldo2=None, ld_extra=0, force_bn=0,
-         force_stages=0, force_splits=0, force_2cta=0, force_persistent=0, rowstats_out=None, ln=None):
+         force_stages=0, force_splits=0, force_2cta=0, force_persistent=0, rowstats_out=None, ln=None,
+         row_scale=None):
     _bump()
     Nn = w.shape[0]
     if mode == EA_GEMM_LINEAR:
@@ -72,6 +73,8 @@ def gemm(a, w, out=None, *, mode=0, M=None, N=None, K=None, lda=None, ldw=0, con
         y = y.reshape(y.shape[0], Nn // 128, 2, 64)
         y = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(y.shape[0], Nn // 2)
     y = y * out_scale
+    if row_scale is not None:
+        y = y * row_scale.reshape(-1, 1)
     if residual is not None:
         y = y + residual.reshape(y.shape).float()
     tgt = out if out is not None else out_f32

@@ -126,3 +126,20 @@ def test_fused_ddim_loop_matches_oracle_loop(use_graph):
     assert err < 5e-2, err
     if use_graph:
         assert eng.launches_per_step > 100
+
+
+def test_guess_mode_and_spatial_scale_map_vs_oracle():
+    """ControlNetModel2.forward scaling variants (utils/stable_diffusion_controlnet.py:777-802) on the CUDA path."""
+    cfg = TINY
+    usd = make_state_dict(cfg, "unet", 41)
+    csds = [make_state_dict(cfg, "controlnet", 42), make_state_dict(cfg, "controlnet", 43)]
+    x, ctx, hints = make_inputs(cfg, 2, 16, 11, 3)
+    eng = DenoiseEngine(cfg, usd, csds, torch.device("cuda:0"))
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    t = 601
+    smap = torch.rand(16, 16, generator=torch.Generator().manual_seed(9))
+    for scales, gm in (([0.7, 1.0], True), ([smap, 0.5], False), ([0.7, 1.0], False)):
+        eng.prepare(ctx, hints, scales, guess_mode=gm)
+        with torch.no_grad():
+            ref = O.apply_model(usd, ut, [(sd, ct) for sd in csds], x, torch.full((2,), t), ctx, hints, scales, guess_mode=gm)
+        assert (eng.eps(x, t).cpu() - ref).abs().max().item() < EPS_TOL

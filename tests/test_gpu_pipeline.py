@@ -127,3 +127,40 @@ def test_pipeline_callback_sees_unblended_latents_and_two_images_per_prompt():
     # and the fused-blend path (no callback) ends in the same place
     lat_f = pipe(generator=torch.manual_seed(5), **kw).images
     _close(lat_f.cpu(), lat.cpu(), "fused blend vs host-side blend")
+
+
+def test_pipeline_with_unipc_scheduler_fused_update():
+    """`pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config)` (editany_lora.py:383,418): the
+    fused device-side multistep update against the reference loop re-enacted with the scheduler object on the oracle
+    networks (alignment_ratio 0.5: the blend re-noises with the scheduler's alpha_t / sigma_t)."""
+    from editanything_b200.schedulers import UniPCMultistepScheduler
+    cfg, usd, csds, vsd, pipe, image, mask, conds, pe, ne = _setup()
+    pipe.scheduler = UniPCMultistepScheduler.from_config(pipe.scheduler.config)
+    for ar in (None, 0.5):
+        lat = pipe(image=image, mask_image=mask, controlnet_conditioning_image=conds, height=128, width=128,
+                   num_inference_steps=STEPS, guidance_scale=GS, prompt_embeds=pe, negative_prompt_embeds=ne,
+                   controlnet_conditioning_scale=[0.5, 1.0], alignment_ratio=ar, num_images_per_prompt=1,
+                   generator=torch.manual_seed(7), output_type="latent").images
+        gen = torch.manual_seed(7)
+        x = torch.randn((1, 4, 16, 16), generator=gen)
+        noise = x
+        with torch.no_grad():
+            mom = V.encode_moments(image, vsd, VCFG)
+        mean, logvar = mom.chunk(2, 1)
+        init = VCFG.scaling_factor * (mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * torch.randn(mean.shape, generator=gen))
+        m = 1 - F.interpolate((mask >= 0.5).float(), (16, 16), mode="nearest")
+        sch = UniPCMultistepScheduler.from_config(DDIMScheduler().config)
+        sch.set_timesteps(STEPS)
+        ts = sch.timesteps
+        ctx = torch.cat([ne, pe])
+        hints = [torch.cat([c] * 2) for c in conds]
+        ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+        for i, t in enumerate(ts):
+            with torch.no_grad():
+                e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], torch.cat([x] * 2), torch.full((2,), int(t)), ctx, hints, [0.5, 1.0])
+            x = sch.step(e[:1] + GS * (e[1:] - e[:1]), t, x).prev_sample
+            if ar is not None and i < len(ts) * ar:
+                x = sch.add_noise(init, noise, ts[i + 1]) * m + x * (1 - m)
+        if ar is None:
+            x = init * m + x * (1 - m)
+        _close(lat.cpu(), x, f"UniPC latents alignment_ratio={ar}")

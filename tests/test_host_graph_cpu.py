@@ -50,3 +50,39 @@ def test_fused_step_matches_ddim_formula():
     x0 = (lat0 - (1 - a[i]) ** 0.5 * e) / a[i] ** 0.5
     xp = ap[i] ** 0.5 * x0 + (1 - ap[i]) ** 0.5 * e
     assert (eng.latents() - xp).abs().max().item() < 1e-4
+
+
+def test_guess_mode_and_spatial_scale_map_match_oracle():
+    """ControlNetModel2.forward scaling variants (utils/stable_diffusion_controlnet.py:777-802): guess mode =
+    logspace(-1, 0, 13) per-residual factors on top of the scale; a tensor scale = a spatial map resized bilinearly
+    (align_corners=True) to every residual's resolution (ea_gemm_args.row_scale)."""
+    import torch
+    from editanything_b200.denoise import DenoiseEngine
+    from editanything_b200.unet_spec import TINY, build_topology, make_state_dict
+    from oracle import unet_oracle as O
+    from oracle.inputs import make_inputs
+    from tests import cpu_ops
+    cfg = TINY
+    usd = make_state_dict(cfg, "unet", 41)
+    csds = [make_state_dict(cfg, "controlnet", 42), make_state_dict(cfg, "controlnet", 43)]
+    x, ctx, hints = make_inputs(cfg, 2, 16, 11, 3)
+    eng = DenoiseEngine(cfg, usd, csds, torch.device("cpu"), backend=cpu_ops)
+    ut, ct = build_topology(cfg), build_topology(cfg, with_decoder=False)
+    t = 601
+    # guess mode
+    eng.prepare(ctx, hints, [0.7, 1.0], guess_mode=True)
+    with torch.no_grad():
+        ref = O.apply_model(usd, ut, [(sd, ct) for sd in csds], x, torch.full((2,), t), ctx, hints, [0.7, 1.0], guess_mode=True)
+        plain = O.apply_model(usd, ut, [(sd, ct) for sd in csds], x, torch.full((2,), t), ctx, hints, [0.7, 1.0])
+    got = eng.eps(x, t)
+    assert (got - ref).abs().max().item() < 2e-4 and (got - plain).abs().max().item() > 1e-3
+    # spatial map on the first net, plain float on the second
+    g = torch.Generator().manual_seed(9)
+    smap = torch.rand(16, 16, generator=g)
+    eng.prepare(ctx, hints, [smap, 0.5])
+    with torch.no_grad():
+        ref = O.apply_model(usd, ut, [(sd, ct) for sd in csds], x, torch.full((2,), t), ctx, hints, [smap, 0.5])
+    assert (eng.eps(x, t) - ref).abs().max().item() < 2e-4
+    # back to plain floats
+    eng.prepare(ctx, hints, [0.7, 1.0])
+    assert (eng.eps(x, t) - plain).abs().max().item() < 2e-4
