@@ -35,12 +35,29 @@ def build_sam_from_state_dict(cfg: SamEncoderConfig, state_dict):
     return sam.eval()
 
 
+def config_from_state_dict(sd):
+    """The encoder configuration a checkpoint was trained with, read off its tensor shapes (the registry keys only
+    name the default sizes; a checkpoint of another size - e.g. the test-sized ones - still loads)."""
+    pe = sd["image_encoder.pos_embed"]
+    grid, dim = pe.shape[1], pe.shape[-1]
+    patch = sd["image_encoder.patch_embed.proj.weight"].shape[-1]
+    depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("image_encoder.blocks."))
+    head_dim = sd["image_encoder.blocks.0.attn.rel_pos_h"].shape[1]
+    lens = [sd[f"image_encoder.blocks.{i}.attn.rel_pos_h"].shape[0] for i in range(depth)]
+    glob = tuple(i for i, n in enumerate(lens) if n == 2 * grid - 1)
+    win = [(n + 1) // 2 for i, n in enumerate(lens) if i not in glob]
+    return SamEncoderConfig(img_size=grid * patch, patch_size=patch, embed_dim=dim, depth=depth, num_heads=dim // head_dim,
+                            mlp_dim=sd["image_encoder.blocks.0.mlp.lin1.weight"].shape[0],
+                            out_chans=sd["image_encoder.neck.0.weight"].shape[0], window_size=win[0] if win else 0,
+                            global_attn_indexes=glob)
+
+
 def _builder(cfg):
     def build(checkpoint=None):
         if checkpoint is None:
             raise ValueError("a checkpoint path is required (synthetic weights: build_sam_from_state_dict)")
         sd = torch.load(checkpoint, map_location="cpu", weights_only=True)
-        return build_sam_from_state_dict(cfg, sd)
+        return build_sam_from_state_dict(config_from_state_dict(sd), sd)
     return build
 
 

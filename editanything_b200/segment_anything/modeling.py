@@ -251,8 +251,9 @@ class _EncoderModule(nn.Module):
         self.img_size = cfg.img_size
 
     def _apply(self, fn, *a, **k):
+        from .. import _backend
         probe = fn(torch.zeros(1))
-        if probe.is_cuda and self.engine is None:
+        if (probe.is_cuda or _backend.OPS is not None) and self.engine is None:     # (OPS: the CPU test-suite's seam)
             from ..sam import SamEncoderEngine
             self.engine = SamEncoderEngine(self.cfg, self._sd, probe.device)
             self._sd = None
