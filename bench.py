@@ -460,8 +460,12 @@ def run_ours(args, rank, world, local_rank):
 
 
 def _oracle_step_fn(cfg):
-    """Builds the CPU oracle step (ControlNet x2 -> UNet -> CFG -> DDIM) at configs[1] size."""
+    """Builds the CPU step (ControlNet x2 -> UNet -> CFG -> DDIM) at configs[1] size: the REFERENCE's own
+    cldm.ControlNet / ControlledUnetModel modules when they are available (oracle/_ref, made by oracle/build_ref.py
+    in the build container and shipped with the snapshot; kind "reference"), else the oracle port (kind "port").
+    Returns (step, kind)."""
     from editanything_b200.unet_spec import build_topology, make_state_dict
+    from oracle import ref_shim
     from oracle import unet_oracle as O
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     usd = {k: v.cpu() for k, v in make_state_dict(cfg, "unet", 101, device=dev).items()}
@@ -470,15 +474,27 @@ def _oracle_step_fn(cfg):
     x, ctx, hints = make_inputs(cfg, 2, 64, 77, 11)
     ts, a, ap = O.make_ddim_schedule(DDIM_STEPS)
     state = {"lat": x[:1].clone(), "i": len(ts) - 1}
+    kind, ref_nets = "port", None
+    if ref_shim.available():
+        try:
+            ref_nets = ref_shim.build_reference_nets(cfg, usd, csds)
+            kind = "reference"
+            usd = csds = None
+        except Exception as e:          # e.g. a missing third-party import on this box: fall back to the port
+            sys.stderr.write(f"reference modules unusable ({type(e).__name__}: {e}); timing the oracle port\n")
 
     def step():
         i = state["i"]
         xx = torch.cat([state["lat"], state["lat"]])
+        tt = torch.full((2,), int(ts[i]))
         with torch.no_grad():
-            e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], xx, torch.full((2,), int(ts[i])), ctx, hints, [0.5, 1.0])
+            if ref_nets is not None:
+                e, _ = ref_shim.reference_apply_model(ref_nets[0], ref_nets[1], xx, tt, ctx, hints, [0.5, 1.0])
+            else:
+                e = O.apply_model(usd, ut, [(sd, ct) for sd in csds], xx, tt, ctx, hints, [0.5, 1.0])
         state["lat"], _ = O.ddim_step(state["lat"], e[:1], e[1:], 9.0, float(a[i]), float(ap[i]))
         state["i"] = i - 1 if i > 0 else len(ts) - 1
-    return step
+    return step, kind
 
 
 def usable_cores():
@@ -527,7 +543,7 @@ def cpu_baseline(sample_steps=1):
     from editanything_b200.unet_spec import SD15
     cores = usable_cores()
     torch.set_num_threads(cores)
-    step = _oracle_step_fn(SD15)
+    step, kind = _oracle_step_fn(SD15)
     step()  # warm-up (allocator, thread pool)
     t0 = time.perf_counter()
     for _ in range(sample_steps):
@@ -535,12 +551,14 @@ def cpu_baseline(sample_steps=1):
     dt = (time.perf_counter() - t0) / sample_steps
     sam_s = _oracle_sam_seconds()
     vae_s = _oracle_vae_seconds()
-    return {"value": round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6), "unit": "images/s", "cores": cores, "kind": "port",
+    return {"value": round(1.0 / (DDIM_STEPS * dt + sam_s + vae_s), 6), "unit": "images/s", "cores": cores, "kind": kind,
+            "step_impl": "the reference's own cldm.ControlNet x2 + ControlledUnetModel (oracle/_ref)" if kind == "reference"
+                         else "oracle port of the reference's ldm/cldm modules",
             "ms_per_step": round(dt * 1e3, 1), "sam_ms_per_image": round(sam_s * 1e3, 1),
             "vae_encode_decode_ms_per_image": round(vae_s * 1e3, 1),
             "sample": f"{sample_steps} full-size fused step(s) (2 ControlNets + UNet + CFG + DDIM, B=2, 64x64, fp32) of the "
-                      f"oracle port on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode + 1 VAE encode + decode of the oracle "
-                      f"port; images/s = 1/(50*step + SAM + VAE)"}
+                      f"CPU arm on {cores} host threads after 1 warm-up + 1 SAM ViT-H encode + 1 VAE encode + decode of the oracle "
+                      f"port (segment_anything / diffusers are absent); images/s = 1/(50*step + SAM + VAE)"}
 
 
 def run_reference(args, rank, world):
@@ -551,7 +569,7 @@ def run_reference(args, rank, world):
     from editanything_b200.unet_spec import SD15
     cores = usable_cores()
     torch.set_num_threads(cores)
-    step = _oracle_step_fn(SD15)
+    step, kind = _oracle_step_fn(SD15)
     budget_s = 240.0
     t0 = time.perf_counter()
     step()
@@ -575,8 +593,10 @@ def run_reference(args, rank, world):
             "value": v, "unit": "images/s", "n_gpus": world, "steps": k, "warmup": 1 + n_w,
             "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic inputs, seeded random weights",
-            "config": {"workload": "BASELINE.json configs[1] on host CPU (reference ldm/cldm algorithm, oracle port)"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "BASELINE.json configs[1]: SD1.5 ControlNet-inpaint 512x512, 50 DDIM steps, batch=1 "
+                                   "(+CFG => B=2), SAM+inpaint ControlNets, L=77 - on the host CPU: " +
+                                   ("the reference's own cldm modules (oracle/_ref)" if kind == "reference" else "oracle port")},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

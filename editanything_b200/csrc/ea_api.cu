@@ -40,6 +40,16 @@ extern "C" void ea_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 void ea_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int ea_sm_count() {
+  static int n_sm[EA_MAX_DEV] = {0};
+  const int d = ea_dev();
+  if (!n_sm[d]) {
+    int n = 0;
+    n_sm[d] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return n_sm[d];
+}
+
 extern "C" int ea_version(void) { return 1; }
 extern "C" const char* ea_dtype_name(void) {
 #ifdef EA_USE_BF16

@@ -747,7 +747,8 @@ static int encode_qkv(CUtensorMap* m, const void* base, int d, int heads, int N,
 template <int NQT, bool BIAS>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnKParams& p, dim3 grid, int smem_bytes, cudaStream_t stream) {
-  static int max_set = 0;
+  static int max_set_dev[EA_MAX_DEV];
+  int& max_set = max_set_dev[ea_dev()];
   if (smem_bytes > max_set) {
     if (cudaFuncSetAttribute(ea_attn_kernel<NQT, BIAS>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
@@ -810,7 +811,8 @@ extern "C" int ea_attention(const ea_attn_args* a, void* stream_) {
     if (encode_qkv(&tk, a->k, a->d, a->heads, a->Nkv, a->B, a->k_ns, a->k_bs, DB_BKV)) return EA_ERR_TMAP;
     if (encode_qkv(&tv, a->v, a->d, a->heads, a->Nkv, a->B, a->v_ns, a->v_bs, DB_BKV)) return EA_ERR_TMAP;
     const int smem_bytes = 2 * AT_ATOM + DB_STAGES * 2 * DB_KVT + (1 + 2 * DB_STAGES + 12) * 8 + 16 + 1024;
-    static int db_set = 0;
+    static int db_set_dev[EA_MAX_DEV];
+    int& db_set = db_set_dev[ea_dev()];
     if (!db_set) {
       if (cudaFuncSetAttribute(ea_attn_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
           cudaSuccess)

@@ -1470,18 +1470,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
   return best;
 }
 
-static int g_n_sm = 0;
-static int sm_count() {
-  if (!g_n_sm) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_n_sm = n;
-    else
-      g_n_sm = 148;
-  }
-  return g_n_sm;
-}
+static int sm_count() { return ea_sm_count(); }
 
 }  // namespace ea
 
@@ -1779,7 +1768,8 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
   if (G == 1) L1.g[0] = L.g[0];
 
   if (use_persist) {
-    static int cache_p[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static int cache_all[EA_MAX_DEV][3][2];     // zero-initialised; per device (see ea_internal.h)
+    int (*cache_p)[2] = cache_all[ea_dev()];
     const long long total = tiles * G;
     const int grid_p = (int)(total < sm_count() ? total : sm_count());
     cudaError_t lp;
@@ -1816,7 +1806,8 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
     const int occ = (2 * (smem_bytes + 1024) <= 227 * 1024 && 2 * tmem_c <= 512) ? 2 : 1;
     if (tiles * G * plan.splits > (long long)occ * sm_count()) return EA_ERR_SHAPE;
   }
-  static int cache_k[2][2] = {{0, 0}, {0, 0}};
+  static int cache_k_all[EA_MAX_DEV][2][2];
+  int (*cache_k)[2] = cache_k_all[ea_dev()];
   cudaError_t le;
   int rc;
   if (two) {

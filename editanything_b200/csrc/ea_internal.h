@@ -12,6 +12,15 @@ typedef CUresult (*ea_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint3
 // Resolved through cudaGetDriverEntryPoint (no link-time libcuda dependency).
 ea_tmap_encode_fn ea_tmap_encode();
 void ea_count_launch();
+// Per-device caches: cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process - a process that
+// drives a second GPU must set / query them there too.  Tables are indexed by ea_dev() (current device, < EA_MAX_DEV).
+#define EA_MAX_DEV 32
+static inline int ea_dev() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d < EA_MAX_DEV ? d : EA_MAX_DEV - 1;
+}
+int ea_sm_count();   // SMs of the current device (cached per device)
 
 // Programmatic dependent launch (PDL): every kernel of this library calls griddepcontrol.wait before
 // it touches global memory, so consecutive launches on a stream may overlap the next kernel's

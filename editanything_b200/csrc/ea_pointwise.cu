@@ -10,7 +10,7 @@ namespace ea {
 // ------------------------------- GroupNorm ---------------------------------
 // ONE launch: every CTA owns a run of pixels of one image, keeps it in shared memory, reduces its
 // per-group sum / sum-of-squares in registers (thread <-> fixed 8-channel vector, so no atomics in
-// the loop), publishes 2*groups partials with global atomics, waits on a per-image arrival counter
+// the loop), publishes its 2*groups partials (plain stores, one slot per CTA), waits on a per-image arrival counter
 // (all CTAs are resident: grid <= #SMs), then normalises + affine (+SiLU) straight out of shared
 // memory.  The tensor is read from HBM/L2 once and written once.  Workspace layout per image b:
 // ws[b*(2G+2) + 0..2G) = {sum, sumsq} per group, then two int counters {arrived, done}; it must be
@@ -55,8 +55,11 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   const int pl = threadIdx.x / nvec;
   const bool active = pl < lanes;
   const int c = v << 3;
-  float* wsb = ws + (long long)b * (2 * groups + 2);
-  int* cnt = reinterpret_cast<int*>(wsb + 2 * groups);
+  // workspace: [B][2] int counters {arrived, done}, then one slot of 2*groups partial sums per (image, CTA): every
+  // CTA publishes its partials with plain stores and every CTA sums them back in the same fixed order - no
+  // floating-point atomics, so the statistics (and everything downstream) are bit-reproducible run to run
+  int* cnt = reinterpret_cast<int*>(ws) + 2 * b;
+  float* pws_b = ws + 2 * gridDim.y + (size_t)b * chunks * (2 * groups);
   // phase 0: fused (pass 1, image-wide spin barrier, pass 2).  phases 1 / 2: the two passes as
   // SEPARATE launches without any inter-CTA wait - used when several streams run concurrently and
   // a spinning, partially resident grid could starve another one (no co-residency guarantee then).
@@ -100,7 +103,7 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
     sh[threadIdx.x] = acc;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&wsb[i], sh[i]);
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) __stcg(&pws_b[(size_t)blockIdx.x * (2 * groups) + i], sh[i]);
   __threadfence();
   __syncthreads();
   if (phase == 1) return;
@@ -120,7 +123,27 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
   // the image's 2*groups statistics come back in ONE L2 round trip (per-thread dependent loads of
   // "its" groups cost several serialized round trips: profiles/r01j_gn_ncu_full.txt)
   __syncthreads();
-  if (threadIdx.x < groups * 2) sh[threadIdx.x] = __ldcg(&wsb[threadIdx.x]);
+  {
+    // sum of the image's per-CTA partials in a fixed order: `parts` threads per statistic take every parts-th CTA
+    // (independent loads: one or two L2 round trips), then one thread per statistic adds the parts in order
+    const int g2 = 2 * groups;
+    int parts = (int)blockDim.x / g2;
+    const int cap = part_bytes / (g2 * (int)sizeof(float));
+    if (parts > cap) parts = cap;
+    if (parts < 1) parts = 1;
+    const int i = threadIdx.x % g2, pidx = threadIdx.x / g2;
+    if (pidx < parts) {
+      float acc = 0.f;
+      for (int cidx = pidx; cidx < chunks; cidx += parts) acc += __ldcg(&pws_b[(size_t)cidx * g2 + i]);
+      part[pidx * g2 + i] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < g2) {
+      float acc = 0.f;
+      for (int q = 0; q < parts; ++q) acc += part[q * g2 + threadIdx.x];
+      sh[threadIdx.x] = acc;
+    }
+  }
   __syncthreads();
   if (active) {
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
@@ -162,12 +185,11 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
                      ea_pack2(vals[4], vals[5]), ea_pack2(vals[6], vals[7]));
     }
   }
-  // ---- leave the workspace zero for the next launch
+  // ---- leave the counters zero for the next launch (the partial slots are simply overwritten)
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (phase == 0 && threadIdx.x == 0) {
     int old = atomicAdd(cnt + 1, 1);
     if (old == chunks - 1) {
-      for (int i = 0; i < groups * 2; ++i) wsb[i] = 0.f;
       cnt[0] = 0;
       cnt[1] = 0;
     }
@@ -802,13 +824,7 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
   const int C1 = a->x2 ? a->C1 : a->C;
   if (a->x2 && (C1 % 8 != 0 || a->ldx2 % 8 != 0)) return EA_ERR_SHAPE;
   cudaStream_t st = EA_STREAM(stream);
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
-      n_sm = 148;
-  }
+  const int n_sm = ea_sm_count();
   if (a->B > n_sm) return EA_ERR_SHAPE;
   int chunks = n_sm / a->B;                 // all CTAs resident (they barrier on each other)
   if (chunks > a->HW) chunks = a->HW;
@@ -822,7 +838,8 @@ extern "C" int ea_groupnorm(const ea_gn_args* a, void* stream) {
   const int part_bytes = ((threads / nvec) * 2 * a->C * 4 + 15) & ~15;
   const int cached = cache_bytes + part_bytes <= 200 * 1024;
   const int smem = 512 + part_bytes + (cached ? (int)cache_bytes : 0);
-  static int max_set = 0;
+  static int max_set_dev[EA_MAX_DEV];
+  int& max_set = max_set_dev[ea_dev()];
   if (smem > max_set) {
     if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
@@ -945,7 +962,8 @@ extern "C" int ea_sam_relpos(const void* q, long long q_bs, long long q_ns, cons
   if (d % 2 != 0 || S <= 0 || S > 128) return EA_ERR_SHAPE;
   const int smem = 2 * S * (d + 1) * (int)sizeof(float);
   if (smem > 200 * 1024) return EA_ERR_SHAPE;
-  static int max_set = 0;
+  static int max_set_dev[EA_MAX_DEV];
+  int& max_set = max_set_dev[ea_dev()];
   if (smem > max_set) {
     if (cudaFuncSetAttribute(sam_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
@@ -1034,7 +1052,8 @@ extern "C" int ea_conv_in(const void* x, const float* w, const float* bias, void
   const ea_half* ad = reinterpret_cast<const ea_half*>(add);
   const long long l1 = ldo > 0 ? ldo : Cout, l2 = ldo2 > 0 ? ldo2 : Cout;
   if (Cin == 4) {
-    static bool set4 = false;
+    static bool set4_dev[EA_MAX_DEV];
+    bool& set4 = set4_dev[ea_dev()];
     if (!set4) {
       if (cudaFuncSetAttribute(conv_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                96 * 1024) != cudaSuccess) return EA_ERR_CUDA;
@@ -1043,7 +1062,8 @@ extern "C" int ea_conv_in(const void* x, const float* w, const float* bias, void
     if (smem > 96 * 1024) return EA_ERR_SHAPE;
     ea_launch(conv_smallcin_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, xx, w, bias, o1, l1, o2, l2, ad, B, H, W, Cout);
   } else {
-    static bool set8 = false;
+    static bool set8_dev[EA_MAX_DEV];
+    bool& set8 = set8_dev[ea_dev()];
     if (!set8) {
       if (cudaFuncSetAttribute(conv_smallcin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                192 * 1024) != cudaSuccess) return EA_ERR_CUDA;

@@ -130,7 +130,7 @@ class DenoiseEngine:
             self.t_dev = torch.zeros(self.B, device=self.dev, dtype=torch.float32)
             self.coef_dev = torch.zeros(16, device=self.dev, dtype=torch.float32)
             self.step_ctr = torch.zeros(1, device=self.dev, dtype=torch.int32)
-            self.gn_ws = torch.zeros(self.B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
+            self.gn_ws = self.ops.gn_workspace(self.B, self.dev)
             self._sched_key, self._sched_cap, self.n_steps = None, 0, 0
             self._graph = None
 

@@ -402,7 +402,7 @@ class UNetRunner:
         """One zeroed GroupNorm workspace per concurrent stream."""
         key = (B, n)
         if key not in self._lane_gn:
-            self._lane_gn[key] = [torch.zeros(B * (32 * 2 + 2), device=self.dev, dtype=torch.float32) for _ in range(n)]
+            self._lane_gn[key] = [self.ops.gn_workspace(B, self.dev) for _ in range(n)]
         return self._lane_gn[key]
 
     def _encoder(self, net: PackedNet, x_half, emb_all, ctxc, gn_ws, guided_hint=None, sinks=None, scale=1.0,
@@ -505,7 +505,7 @@ class UNetRunner:
         B, H, W_, _ = x_half.shape
         key = (n * B,)
         if key not in self._ls_ws:
-            self._ls_ws[key] = torch.zeros(n * B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
+            self._ls_ws[key] = o.gn_workspace(n * B, self.dev)
         gn_ws = self._ls_ws[key]
 
         def zero_convs(h, i, slot):
@@ -581,7 +581,7 @@ class UNetRunner:
         o = self.ops
         B, H, W_, _ = x_half.shape
         if gn_ws is None:
-            gn_ws = torch.zeros(B * (32 * 2 + 2), device=self.dev, dtype=torch.float32)
+            gn_ws = o.gn_workspace(B, self.dev)
         sinks = self.alloc_sinks(B, H, W_)
         if embs is None:
             embs = self.compute_embs(t_dev, B)

@@ -164,6 +164,11 @@ def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_str
     return out
 
 
+def gn_workspace(B, device, groups=32):
+    """Zeroed ea_groupnorm workspace for B images (EA_GN_WS_FLOATS: counters + one partial slot per (image, CTA))."""
+    return torch.zeros(2 * B + 2 * groups * 256, device=device, dtype=torch.float32)
+
+
 def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True, workspace=None,
               x2=None, C1=0, ldx=None, ldx2=None, ldo=None):
     lib = L.lib()
@@ -186,7 +191,7 @@ def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True,
     g.eps, g.silu = eps, 1 if silu else 0
     g.two_pass = 1 if _CONCURRENT[0] else 0
     if workspace is None:
-        workspace = torch.zeros(B * (groups * 2 + 2), device=x.device, dtype=torch.float32)
+        workspace = gn_workspace(B, x.device, groups)
     g.workspace = workspace.data_ptr()
     L.check(lib.ea_groupnorm(C.byref(g), _stream()), "ea_groupnorm")
     return out

@@ -19,10 +19,13 @@ in-container HF port transformers/models/sam/modeling_sam.py, "HF:"):
                                                      (implicit GEMM) -> LayerNorm2d
 Activations are channels-last half [tokens, C]; all accumulation fp32.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from ._backend import default_ops
+from ._graphs import GraphLRU
 from .sam_spec import SAM_TINY, SAM_VIT_H, SamEncoderConfig, make_sam_state_dict  # noqa: F401
 
 
@@ -64,7 +67,7 @@ class SamEncoderEngine:
         w["neck3.g"], w["neck3.b"] = F(sd["neck.3.weight"]), F(sd["neck.3.bias"])
         self.w = w
         self._bufs = {}
-        self._graphs = {}
+        self._graphs = GraphLRU(int(os.environ.get("EA_GRAPH_CACHE", "4")))
 
     def _half(self, t):
         return t.detach().to(device=self.dev, dtype=self.hdt).contiguous()
@@ -166,7 +169,7 @@ class SamEncoderEngine:
             with torch.cuda.graph(g):
                 static_out = self._encode_eager(static_in)
             st = (g, static_in, static_out)
-            self._graphs[B] = st
+            self._graphs.put(B, st)
         g, static_in, static_out = st
         static_in.copy_(img, non_blocking=True)
         g.replay()

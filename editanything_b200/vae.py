@@ -23,10 +23,13 @@ output channels so it can use the same GEMM; `ea_image_out` drops the padding, a
 """
 import types
 
+import os
+
 import torch
 
 from . import _lib as L
 from ._backend import default_ops
+from ._graphs import GraphLRU
 from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, encoder_blocks, make_vae_state_dict  # noqa: F401
 
 
@@ -45,7 +48,7 @@ class _VaeBase:
                                             block_out_channels=cfg.block_out_channels)
         self.w = {}
         self._gn_ws = {}
-        self._graphs = {}
+        self._graphs = GraphLRU(int(os.environ.get("EA_GRAPH_CACHE", "4")))
 
     def _pack_blocks(self, sd, blocks):
         H, F, w = self._half, self._f32, self.w
@@ -85,7 +88,7 @@ class _VaeBase:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = fn(static_in)
-            st = self._graphs[key] = (g, static_in, static_out)
+            st = self._graphs.put(key, (g, static_in, static_out))
         g, static_in, static_out = st
         static_in.copy_(x, non_blocking=True)
         g.replay()
@@ -108,7 +111,7 @@ class _VaeBase:
         out = self._new(B * HW, C_)
         ws = self._gn_ws.get(B)      # zero-initialised once; the kernel leaves it zeroed for the next launch
         if ws is None:
-            ws = self._gn_ws[B] = torch.zeros(B * (self.cfg.num_groups * 2 + 2), device=self.dev, dtype=torch.float32)
+            ws = self._gn_ws[B] = self.ops.gn_workspace(B, self.dev, self.cfg.num_groups)
         self.ops.groupnorm(x, g, b, out, B=B, HW=HW, C_=C_, groups=self.cfg.num_groups, eps=self.cfg.eps,
                            silu=silu, workspace=ws)
         return out

@@ -172,6 +172,7 @@ int ea_attention(const ea_attn_args* args, void* stream);
  *   (skip-concat, cldm/cldm.py:39-41); pass x2 = NULL for a single source.
  * ea_layernorm: nn.LayerNorm over the last dim of [M, C]  (attention.py:263-265).
  */
+#define EA_GN_WS_FLOATS(B, groups) (2 * (B) + 2 * (groups) * 256)
 typedef struct ea_gn_args {
   const void* x; long long ldx; int C1;
   const void* x2; long long ldx2;
@@ -181,8 +182,10 @@ typedef struct ea_gn_args {
   float eps; int silu;
   int two_pass;              /* 1: statistics and normalisation as two launches with no inter-CTA wait
                                 (required when other streams run kernels concurrently) */
-  float* workspace;          /* >= B*(2*groups+2) floats, ZERO before the first call (the kernel
-                                leaves it zero); one workspace may serve every call on a stream */
+  float* workspace;          /* >= 2*B + 2*groups*256 floats (EA_GN_WS_FLOATS), ZERO before the first call (the
+                                kernel leaves its counters zero); one workspace may serve every call on a stream.
+                                Layout: [B][2] int arrival counters, then one slot of 2*groups partial sums per
+                                (image, CTA) - no floating-point atomics: results are bit-reproducible */
   int n_nets;                /* 0 / 1: one gamma / beta for all B images.  2 / 3: the images are n_nets stacked
                                 batches of B / n_nets (the same layer of the UNet encoder and the ControlNets,
                                 see ea_gemm_grouped); batch g > 0 uses gamma_more[g-1] / beta_more[g-1] */

@@ -10,6 +10,9 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("EA_REFERENCE_ROOT", "/root/reference")
+_LOCAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py (travels to the GPU box)
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "cldm")) and os.path.isdir(os.path.join(_LOCAL, "cldm")):
+    REFERENCE_ROOT = _LOCAL
 
 
 def available():

@@ -114,6 +114,10 @@ def attention(q, k, v, out, *, B, heads, Nq, Nkv, d, q_strides, k_strides, v_str
     return out
 
 
+def gn_workspace(B, device, groups=32):
+    return torch.zeros(2 * B + 2 * groups * 256, device=device, dtype=torch.float32)
+
+
 def groupnorm(x, gamma, beta, out, *, B, HW, C_, groups=32, eps=1e-5, silu=True, workspace=None, x2=None,
               C1=0, ldx=None, ldx2=None, ldo=None):
     _bump(2)

@@ -3,7 +3,9 @@ needs minutes at these sizes): finiteness, batch-permutation equivariance and CF
 consistency of the fused eps network.
   configs[2]: SD2.1 (cldm_v21.yaml: 64-wide heads, linear proj_in/out, ctx 1024) 768x768, N = 4 (+CFG => B = 8)
   configs[4]: SD1.5 1024x1024 tile refinement (128x128 latents, 16384 tokens at the top level), N = 1
-Tolerance 5e-3: GroupNorm statistics are summed with fp32 atomics whose order varies between launches."""
+Tolerance 5e-3 for the permuted batch: the GroupNorm CTA <-> image assignment (and with it the fixed summation order
+of the per-CTA partials) follows the batch position, so a permuted batch sums in another order; the same batch twice
+is bit-identical (asserted below)."""
 import pytest
 import torch
 
@@ -37,6 +39,7 @@ def test_sd21_768_batch4_permutation_equivariance():
     e1 = eng.eps(x[perm], 501).cpu()
     err = (e1 - e0[perm]).abs().max().item()
     assert err < 5e-3, err
+    assert torch.equal(eng.eps(x[perm], 501).cpu(), e1)          # run-to-run: bit-identical
 
 
 def test_sd15_1024_cfg_duplicate_consistency():

@@ -86,3 +86,12 @@ def test_guess_mode_and_spatial_scale_map_match_oracle():
     # back to plain floats
     eng.prepare(ctx, hints, [0.7, 1.0])
     assert (eng.eps(x, t) - plain).abs().max().item() < 2e-4
+
+
+def test_graph_cache_is_a_bounded_lru():
+    from editanything_b200._graphs import GraphLRU
+    c = GraphLRU(2)
+    c.put("a", 1), c.put("b", 2)
+    assert c.get("a") == 1            # refreshes "a"
+    c.put("c", 3)                     # evicts "b", the least recently used
+    assert "b" not in c and "a" in c and "c" in c and len(c) == 2 and c.get("b") is None

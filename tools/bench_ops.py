@@ -136,7 +136,7 @@ def bench_norm():
         x = torch.randn(B, H, H, C_, device="cuda").to(dt)
         y = torch.empty_like(x)
         g, b = torch.randn(C_, device="cuda"), torch.randn(C_, device="cuda")
-        ws = torch.zeros(B * 66, device="cuda")
+        ws = ops.gn_workspace(B, "cuda")
         us = timeit(lambda: ops.groupnorm(x, g, b, y, B=B, HW=H * H, C_=C_, workspace=ws))
         out.append({"op": "groupnorm", "case": name, "us": round(us, 1), "gbs": round(2 * x.numel() * 2 / us / 1e3, 1)})
         print(json.dumps(out[-1]), flush=True)

@@ -723,7 +723,7 @@ def case_groupnorm_stacked_nets():
     gam = [1 + 0.2 * torch.randn(C_, device="cuda") for _ in range(n)]
     bet = [0.2 * torch.randn(C_, device="cuda") for _ in range(n)]
     out = torch.empty_like(x)
-    ws = torch.zeros(n * B * 66, device="cuda")
+    ws = ops.gn_workspace(n * B, "cuda")
     ops.groupnorm(x, gam, bet, out, B=n * B, HW=H * H, C_=C_, eps=1e-5, silu=True, workspace=ws)
     torch.cuda.synchronize()
     xs = x.float().permute(0, 3, 1, 2)
