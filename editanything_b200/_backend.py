@@ -12,3 +12,19 @@ def default_ops():
         return OPS
     from . import ops
     return ops
+
+
+def engine_call(fn):
+    """Decorator for the engines' entry points: run with autograd off but NOT in inference mode.  The reference wraps
+    its request handler in `@torch.inference_mode()` (editany_lora.py:609); tensors created there are inference
+    tensors, and the engines keep persistent buffers (CUDA-graph static inputs, latents, history) that later calls -
+    possibly outside inference mode - update in place, which PyTorch forbids for inference tensors."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        with torch.inference_mode(False), torch.no_grad():
+            return fn(*a, **k)
+    return wrapper

@@ -10,7 +10,7 @@ import math
 import numpy as np
 import torch
 
-from ._backend import default_ops
+from ._backend import default_ops, engine_call
 from .nets import PackedNet, UNetRunner
 from .unet_spec import UNetConfig
 
@@ -53,6 +53,8 @@ class DenoiseEngine:
             old.copy_(new)
             return old
         self._graph = None
+        if torch.is_tensor(new) and new.is_inference():
+            new = new.clone()         # a caller under torch.inference_mode(): persistent buffers must be normal tensors
         setattr(self, name, new)
         return new
 
@@ -80,6 +82,7 @@ class DenoiseEngine:
             out["maps"] = maps
         return out
 
+    @engine_call
     def prepare(self, ctx, hints, scales, guess_mode=False):
         """ctx: [B, L, D] prompt embeddings ([negative; positive] stacked for CFG,
         utils/stable_diffusion_controlnet_inpaint.py:1339-1347); hints: list of NCHW conditioning
@@ -152,6 +155,7 @@ class DenoiseEngine:
             buf.copy_(r)
 
     # -- the sampling schedule as device tables -------------------------------------------------
+    @engine_call
     def set_schedule(self, timesteps, alphas, alphas_prev, blend=None, multistep=None):
         """Everything that changes from step to step of the loop (utils/...inpaint.py:1540-1656), as device
         tables with one row per step: the DDIM coefficients (cldm/ddim_hacked.py:203-231), the per-ResBlock
@@ -189,6 +193,7 @@ class DenoiseEngine:
         self._sched_key = key
 
     # -- parity API: the network output itself ------------------------------------------------
+    @engine_call
     def eps(self, x_nchw, t):
         """eps = unet(x, t, ctx, control=sum_k scale_k * controlnet_k(x, hint_k, t, ctx)) as fp32
         NCHW - the quantity the reference calls `noise_pred` before guidance."""
@@ -214,6 +219,7 @@ class DenoiseEngine:
                               mask=self.mask, lat_half_out=self.x_half, step_counter=self.step_ctr, hist=self.hist,
                               Nimg=self.B // 2, H=H, W=W_, C_=self.cfg.model_channels)
 
+    @engine_call
     def begin(self, latents_nchw, guidance, known_nchw=None, mask_n1hw=None, noise_nchw=None, use_graph=True):
         """latents: fp32 [N, 4, h, w] initial noise (N = B/2 images).  known/mask: optional inpaint blend
         tensors (mask == 1 keeps `known`, utils/...inpaint.py:1484-1489,1647-1664); noise: the initial latent
@@ -227,13 +233,14 @@ class DenoiseEngine:
         if getattr(self, "guidance", None) != float(guidance):
             self._graph = None
         self.guidance = float(guidance)
-        zeros = torch.zeros_like(lat)
-        self._keep("known", nhwc(known_nchw) if known_nchw is not None else zeros)
-        self._keep("noise", nhwc(noise_nchw) if noise_nchw is not None else zeros)
+        # (each buffer gets its OWN zeros: _keep adopts the tensor it is given on first use, and known / noise / mask
+        # must never alias)
+        self._keep("known", nhwc(known_nchw) if known_nchw is not None else torch.zeros_like(lat))
+        self._keep("noise", nhwc(noise_nchw) if noise_nchw is not None else torch.zeros_like(lat))
         if known_nchw is not None:
             m = mask_n1hw.to(self.dev, torch.float32).reshape(lat.shape[0], lat.shape[1], lat.shape[2]).contiguous()
         else:
-            m = zeros[..., 0].contiguous()
+            m = torch.zeros(lat.shape[:3], device=self.dev, dtype=torch.float32)
         self._keep("mask", m)
         # history of the multistep schedulers (x0 predictions of the two previous steps, previous corrected sample)
         self._keep("hist", torch.zeros((3,) + tuple(lat.shape), device=self.dev, dtype=torch.float32))
@@ -243,10 +250,12 @@ class DenoiseEngine:
         self._use_graph = use
         self.step_ctr.zero_()
 
+    @engine_call
     def end_blend(self):
         """Close the blend window from the host (callers that drive the blend themselves)."""
         self.mask.zero_()
 
+    @engine_call
     def blend_now(self, k_init, k_noise):
         """latents = (k_init * known + k_noise * noise) * mask + latents * (1 - mask), outside the fused step
         (utils/...inpaint.py:1647-1656) - for callers that must observe the un-blended latents first."""
@@ -254,9 +263,11 @@ class DenoiseEngine:
         self.lat.copy_((k_init * self.known + k_noise * self.noise) * m + self.lat * (1 - m))
         self.x_half.copy_(torch.cat([self.lat, self.lat]).to(self.hdt))
 
+    @engine_call
     def set_known(self, known_nchw):
         self.known.copy_(known_nchw.to(self.dev, torch.float32).permute(0, 2, 3, 1))
 
+    @engine_call
     def step(self, t=None, a_t=None, a_prev=None):
         """One fused step.  Without arguments: step number *step_ctr of the schedule given to set_schedule()
         (host work: one graph launch).  With (t, a_t, a_prev): a single DDIM (eta=0) step at timestep t
@@ -291,5 +302,6 @@ class DenoiseEngine:
             self.step_ctr.copy_(c0)
         self._graph.replay()
 
+    @engine_call
     def latents(self):
         return self.lat.permute(0, 3, 1, 2).contiguous()

@@ -24,7 +24,7 @@ import os
 import torch
 
 from . import _lib as L
-from ._backend import default_ops
+from ._backend import default_ops, engine_call
 from ._graphs import GraphLRU
 from .sam_spec import SAM_TINY, SAM_VIT_H, SamEncoderConfig, make_sam_state_dict  # noqa: F401
 
@@ -146,6 +146,7 @@ class SamEncoderEngine:
             x = self._block(i, x, B)
         return x
 
+    @engine_call
     def encode(self, img, use_graph=True):
         """img: fp32 [B, 3, S, S] preprocessed (Sam.preprocess) -> fp32 [B, out_chans, S/16, S/16].
         On the CUDA backend the ~320 launches of one encode are captured once per batch size into a

@@ -28,7 +28,7 @@ import os
 import torch
 
 from . import _lib as L
-from ._backend import default_ops
+from ._backend import default_ops, engine_call
 from ._graphs import GraphLRU
 from .vae_spec import SD_VAE, VAE_TINY, VaeConfig, decoder_blocks, encoder_blocks, make_vae_state_dict  # noqa: F401
 
@@ -179,11 +179,13 @@ class VaeDecoderEngine(_VaeBase):
         w["cout.w"], w["cout.b"] = H(cop), F(bop)
         self.last_ch = last
 
+    @engine_call
     def decode(self, z):
         """z: [B, z_channels, h, w] (already divided by scaling_factor) -> object with
         `.sample` = fp32 [B, 3, 8h, 8w] in the decoder's native range (about [-1, 1])."""
         return types.SimpleNamespace(sample=self._decode(z, post=False))
 
+    @engine_call
     def decode_latents(self, latents, use_graph=True):
         """latents as the denoising loop leaves them -> fp32 [B, 3, 8h, 8w] in [0, 1]
         (decode_latents up to the .cpu().permute().numpy() plumbing).  On the CUDA backend the ~170
@@ -272,6 +274,7 @@ class VaeEncoderEngine(_VaeBase):
         if (2 * cfg.z_channels) % 8 != 0:
             raise ValueError("2 * z_channels must be a multiple of 8 (GEMM output width)")
 
+    @engine_call
     def encode(self, x, use_graph=True):
         if x.dim() != 4 or x.shape[1] != self.in_ch:
             raise ValueError(f"expected [B, {self.in_ch}, H, W], got {tuple(x.shape)}")

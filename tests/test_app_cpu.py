@@ -231,3 +231,23 @@ def test_process_end_to_end_on_tiny_engines_from_input_data_pkl(tmp_path, monkey
     assert all(np.array_equal(np.array(a), np.array(b)) for a, b in zip(output + refined, again[1] + again[0]))   # seeded
     with pytest.raises(NotImplementedError):
         model.process(*data["args"], **{**data["kwargs"], "ref_image": {"image": None, "mask": None}})
+
+
+def test_engines_survive_inference_mode_callers():
+    """`process` runs under @torch.inference_mode() like the reference (editany_lora.py:609); engine buffers created
+    during such a call must stay usable from a later call outside inference mode (in-place updates)."""
+    from editanything_b200.denoise import DenoiseEngine
+    from editanything_b200.unet_spec import TINY, make_state_dict
+    from oracle.inputs import make_inputs
+    from tests import cpu_ops
+    eng = DenoiseEngine(TINY, make_state_dict(TINY, "unet", 1), [make_state_dict(TINY, "controlnet", 2)], torch.device("cpu"),
+                        backend=cpu_ops)
+    x, ctx, hints = make_inputs(TINY, 2, 8, 7, 1, n_controlnets=1)
+    with torch.inference_mode():
+        eng.prepare(ctx, hints, [1.0])
+        eng.begin(x[:1], 5.0, use_graph=False)
+        eng.step(501, 0.3, 0.4)
+    eng.prepare(ctx, hints, [1.0])                 # outside: copies into the buffers created above
+    eng.begin(x[:1], 5.0, use_graph=False)
+    eng.step(481, 0.32, 0.42)
+    assert not eng.lat.is_inference() and torch.isfinite(eng.latents()).all()
