@@ -188,25 +188,70 @@ __device__ __forceinline__ void stage_flush(const uint4* stg, int lane, ea_half*
                                             ea_half* out2, long long ldo2, long long m_mine, bool ok_mine,
                                             int col0, int pieces, int n_limit, long long lin_m0, int M) {
   __syncwarp();
+  // Straight-line on purpose: the eight 16-byte pieces of a lane are loaded from the staging block first (8 LDS in
+  // flight) and stored with addresses advanced by a constant row stride.  The rolled version spent ~50 instructions
+  // per 16-byte store on 64-bit multiplies, shuffle-or-linear branches and reconvergence barriers - 22 % of all
+  // instructions a linear GEMM executed (profiles/r02c_gemm_ncu_source_hot.txt).
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = col0 + piece * 8;
-#pragma unroll 1   // rolled on purpose: run once per 64 columns from a cold instruction cache
+  const bool col_ok = piece < pieces && col < n_limit;
+  uint4 val[8];
+#pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + rsub;
-    long long m_r;
-    int ok_r;
-    if (lin_m0 >= 0) {   // linear GEMM: the warp's rows are consecutive - no shuffles on the latency chain
-      m_r = lin_m0 + row;
-      ok_r = m_r < M;
-    } else {
-      m_r = __shfl_sync(0xffffffffu, m_mine, row);
-      ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
+    val[i] = stg[row * 8 + (piece ^ (row & 7))];
+  }
+  if (lin_m0 >= 0) {   // linear GEMM: the warp's rows are consecutive
+    const long long m0 = lin_m0 + rsub;
+    ea_half* ptr = out + m0 * ldo + col;
+    ea_half* ptr2 = out2 ? out2 + m0 * ldo2 + col : nullptr;
+    const long long step = 4 * ldo, step2 = 4 * ldo2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (col_ok && m0 + 4 * i < M) {
+        *reinterpret_cast<uint4*>(ptr) = val[i];
+        if (ptr2) *reinterpret_cast<uint4*>(ptr2) = val[i];
+      }
+      ptr += step;
+      if (ptr2) ptr2 += step2;
     }
-    if (ok_r && piece < pieces && col < n_limit) {
-      const uint4 val = stg[row * 8 + (piece ^ (row & 7))];
-      *reinterpret_cast<uint4*>(out + m_r * ldo + col) = val;
-      if (out2) *reinterpret_cast<uint4*>(out2 + m_r * ldo2 + col) = val;
+  } else {             // convolution tiles: a row's pixel comes from the lane that owns it
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rsub;
+      const long long m_r = __shfl_sync(0xffffffffu, m_mine, row);
+      const int ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
+      if (ok_r && col_ok) {
+        *reinterpret_cast<uint4*>(out + m_r * ldo + col) = val[i];
+        if (out2) *reinterpret_cast<uint4*>(out2 + m_r * ldo2 + col) = val[i];
+      }
     }
+  }
+  __syncwarp();
+}
+
+// The same for a 32-column group (64 bytes per row): four lanes per row, eight rows per pass, four passes - the 64-column
+// mapping would leave half of the lanes idle for twice as many passes (the GEGLU epilogue of the 8-warp persistent
+// kernel flushes 32 output columns per warp-group chunk).  Linear GEMMs only.
+__device__ __forceinline__ void stage_flush32(const uint4* stg, int lane, ea_half* out, long long ldo, int col0,
+                                              int n_limit, long long lin_m0, int M) {
+  __syncwarp();
+  const int piece = lane & 3, rsub = lane >> 2;
+  const int col = col0 + piece * 8;
+  const bool col_ok = col < n_limit;
+  uint4 val[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + rsub;
+    val[i] = stg[row * 8 + (piece ^ (row & 7))];
+  }
+  const long long m0 = lin_m0 + rsub;
+  ea_half* ptr = out + m0 * ldo + col;
+  const long long step = 8 * ldo;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col_ok && m0 + 8 * i < M) *reinterpret_cast<uint4*>(ptr) = val[i];
+    ptr += step;
   }
   __syncwarp();
 }
@@ -243,18 +288,21 @@ __device__ __forceinline__ void epilogue_geglu32(const float* cb, int half_bn, i
                                                  float ln_nm) {
   uint32_t packed[16];
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float2 bx = *reinterpret_cast<const float2*>(cb + c + j);
-    float2 bg = *reinterpret_cast<const float2*>(cb + half_bn + c + j);
+  for (int j = 0; j < 32; j += 4) {     // 16-byte shared-memory loads: the per-column vectors are warp broadcasts
+    float4 bx = *reinterpret_cast<const float4*>(cb + c + j);
+    float4 bg = *reinterpret_cast<const float4*>(cb + half_bn + c + j);
     if (ln) {
-      const float2 gx = *reinterpret_cast<const float2*>(cb + 256 + c + j);
-      const float2 gg = *reinterpret_cast<const float2*>(cb + 256 + half_bn + c + j);
-      bx.x = fmaf(ln_nm, gx.x, bx.x); bx.y = fmaf(ln_nm, gx.y, bx.y);
-      bg.x = fmaf(ln_nm, gg.x, bg.x); bg.y = fmaf(ln_nm, gg.y, bg.y);
+      const float4 gx = *reinterpret_cast<const float4*>(cb + 256 + c + j);
+      const float4 gg = *reinterpret_cast<const float4*>(cb + 256 + half_bn + c + j);
+      bx.x = fmaf(ln_nm, gx.x, bx.x); bx.y = fmaf(ln_nm, gx.y, bx.y); bx.z = fmaf(ln_nm, gx.z, bx.z); bx.w = fmaf(ln_nm, gx.w, bx.w);
+      bg.x = fmaf(ln_nm, gg.x, bg.x); bg.y = fmaf(ln_nm, gg.y, bg.y); bg.z = fmaf(ln_nm, gg.z, bg.z); bg.w = fmaf(ln_nm, gg.w, bg.w);
     }
     const float x0 = fmaf(fx[j], ln_r, bx.x), x1 = fmaf(fx[j + 1], ln_r, bx.y);
+    const float x2 = fmaf(fx[j + 2], ln_r, bx.z), x3 = fmaf(fx[j + 3], ln_r, bx.w);
     const float g0 = fmaf(fg[j], ln_r, bg.x), g1 = fmaf(fg[j + 1], ln_r, bg.y);
+    const float g2 = fmaf(fg[j + 2], ln_r, bg.z), g3 = fmaf(fg[j + 3], ln_r, bg.w);
     packed[j >> 1] = ea_pack2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+    packed[(j >> 1) + 1] = ea_pack2(x2 * gelu_erf_f(g2), x3 * gelu_erf_f(g3));
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q)
@@ -983,7 +1031,9 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // epilogue is instruction-latency bound (3-5 us per tile, profiles/r01p_exp_step_chain_gemm_in_context.txt);
 // a second warp on the same scheduler hides it, also for grids of a single wave.
 template <int EPI_WG, int NG>
-__global__ void __launch_bounds__(64 + 128 * EPI_WG, 1)
+// 320 threads x 200 registers = 64000 of the SM's 65536: ptxas, left alone with __launch_bounds__(320, 1), stopped at
+// 168 and spilled the double-buffered TMEM drain (va / vb) to local memory inside the epilogue loop
+__global__ void __launch_bounds__(64 + 128 * EPI_WG) __maxnreg__(EPI_WG == 2 ? 200 : 255)
 ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int tiles_per_group, const int m_tiles,
                           const int n_groups) {
   // the tile list runs over (group, tile): every group has the same shape and plan; `p` below = the shared fields
@@ -1199,16 +1249,10 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       if (!geglu) {
         const float* cbr = cbt + ((!ln && ri.batch != b_first) ? 256 : 0);
         // this warp-group's chunks: both halves of the 64-column groups wg, wg + EPI_WG, ...; the next chunk's
-        // tcgen05.ld is in flight while the current one is converted and stored
-        uint32_t va[32], vb[32];
-        int c = wg * 64;
-        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, vb);
-        while (c < p.BN) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) va[j] = vb[j];
-          const int nc = ((c & 32) == 0 && c + 32 < p.BN) ? c + 32 : (c & ~63) + GSTEP;
-          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
+        // tcgen05.ld is in flight while the current one is converted and stored.  The two register buffers are
+        // used alternately (ping-pong) instead of moving 32 registers per chunk.
+        auto next_chunk = [&](int c) { return ((c & 32) == 0 && c + 32 < p.BN) ? c + 32 : (c & ~63) + GSTEP; };
+        auto process = [&](const uint32_t (&v)[32], const int c) {
           const int n_first = ncol0 + c;
           const int half = (c >> 5) & 1;
           if (has_res && half == 0) {
@@ -1229,19 +1273,19 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
               for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(cbt + c + j);
                 const float4 g4 = *reinterpret_cast<const float4*>(cbt + 256 + c + j);
-                f[j] = fmaf(__uint_as_float(va[j]), ln_r, fmaf(ln_nm, g4.x, b4.x));
-                f[j + 1] = fmaf(__uint_as_float(va[j + 1]), ln_r, fmaf(ln_nm, g4.y, b4.y));
-                f[j + 2] = fmaf(__uint_as_float(va[j + 2]), ln_r, fmaf(ln_nm, g4.z, b4.z));
-                f[j + 3] = fmaf(__uint_as_float(va[j + 3]), ln_r, fmaf(ln_nm, g4.w, b4.w));
+                f[j] = fmaf(__uint_as_float(v[j]), ln_r, fmaf(ln_nm, g4.x, b4.x));
+                f[j + 1] = fmaf(__uint_as_float(v[j + 1]), ln_r, fmaf(ln_nm, g4.y, b4.y));
+                f[j + 2] = fmaf(__uint_as_float(v[j + 2]), ln_r, fmaf(ln_nm, g4.z, b4.z));
+                f[j + 3] = fmaf(__uint_as_float(v[j + 3]), ln_r, fmaf(ln_nm, g4.w, b4.w));
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(cbr + c + j);
-                f[j] = __uint_as_float(va[j]) + b4.x;
-                f[j + 1] = __uint_as_float(va[j + 1]) + b4.y;
-                f[j + 2] = __uint_as_float(va[j + 2]) + b4.z;
-                f[j + 3] = __uint_as_float(va[j + 3]) + b4.w;
+                f[j] = __uint_as_float(v[j]) + b4.x;
+                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
               }
             }
             if (p.act == EA_ACT_SILU) {
@@ -1280,6 +1324,21 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
           if (half == 1 || c + 32 >= p.BN)
             stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
                         half == 1 ? 8 : 4, p.N, lin_m0, p.M);
+        };
+        uint32_t va[32], vb[32];
+        int c = wg * 64;
+        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, va);
+        while (c < p.BN) {
+          tmem_ld_wait();
+          int nc = next_chunk(c);
+          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
+          process(va, c);
+          c = nc;
+          if (c >= p.BN) break;
+          tmem_ld_wait();
+          nc = next_chunk(c);
+          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, va);
+          process(vb, c);
           c = nc;
         }
       } else if (EPI_WG == 1) {
@@ -1312,7 +1371,10 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
           uint4 o[4];
           epilogue_geglu32(cbt, half_bn, c, fx, fg, o, ln, ln_r, ln_nm);
           stage_put32(stg, lane, 0, o);
-          stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c, 4, p.N >> 1, lin_m0, p.M);
+          if (lin_m0 >= 0)
+            stage_flush32(stg, lane, p.out, p.ldo, (ncol0 >> 1) + c, p.N >> 1, lin_m0, p.M);
+          else
+            stage_flush(stg, lane, p.out, p.ldo, nullptr, 0, ri.m, ri.ok, (ncol0 >> 1) + c, 4, p.N >> 1, lin_m0, p.M);
         }
       }
       // every tcgen05.ld of this accumulator has completed (tmem_ld_wait above): hand it back

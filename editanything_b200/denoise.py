@@ -83,7 +83,7 @@ class DenoiseEngine:
         return out
 
     @engine_call
-    def prepare(self, ctx, hints, scales, guess_mode=False):
+    def prepare(self, ctx, hints, scales, guess_mode=False, cfg_duplicated=False):
         """ctx: [B, L, D] prompt embeddings ([negative; positive] stacked for CFG,
         utils/stable_diffusion_controlnet_inpaint.py:1339-1347); hints: list of NCHW conditioning
         images [B, 3, 8h, 8w] (un-normalised, editany_lora.py:771-778,814-828); scales: list."""
@@ -112,7 +112,15 @@ class DenoiseEngine:
         else:
             self.ctx_cache = caches
             self._graph = None
-        new_hints = [c.precompute_hint(h.to(self.dev)) for c, h in zip(self.cns, hints)]
+        # cfg_duplicated: the conditioning images are [x; x] (prepare_controlnet_conditioning_image doubles them for
+        # classifier-free guidance, utils/...inpaint.py:380-381) - run the hint stack on one half only
+        if cfg_duplicated and all(h.shape[0] % 2 == 0 for h in hints):
+            new_hints = []
+            for c, h in zip(self.cns, hints):
+                g = c.precompute_hint(h[:h.shape[0] // 2].to(self.dev))
+                new_hints.append(torch.cat([g, g]))
+        else:
+            new_hints = [c.precompute_hint(h.to(self.dev)) for c, h in zip(self.cns, hints)]
         old_h = getattr(self, "hints", None)
         if old_h is not None and len(old_h) == len(new_hints) and all(o.shape == n.shape for o, n in zip(old_h, new_hints)):
             for o, n in zip(old_h, new_hints):

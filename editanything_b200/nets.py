@@ -104,6 +104,19 @@ class PackedNet:
                 p = f"input_hint_block.{2 * i}"
                 self.w[p + ".w"] = F(sd[p + ".weight"].permute(2, 3, 1, 0))
                 self.w[p + ".b"] = F(sd[p + ".bias"])
+                if i > 0:
+                    # tensor-core form of layers 2..8: channels zero-padded to multiples of 64 (the implicit-GEMM
+                    # convolution needs Cin % 64 == 0); padded output channels get zero weights and bias, so they
+                    # stay exactly 0 through SiLU and feed zeros into the next layer's padded inputs
+                    wt = sd[p + ".weight"]
+                    co, ci = wt.shape[0], wt.shape[1]
+                    co_p = co if i == len(HINT_STRIDES) - 1 else -(-co // 64) * 64
+                    ci_p = -(-ci // 64) * 64
+                    wp = torch.zeros(co_p, 3, 3, ci_p, dtype=wt.dtype, device=wt.device)
+                    wp[:co, :, :, :ci] = wt.permute(0, 2, 3, 1)
+                    bp = torch.zeros(co_p, dtype=wt.dtype, device=wt.device)
+                    bp[:co] = sd[p + ".bias"]
+                    self.w[p + ".wp"], self.w[p + ".bp"] = H(wp.reshape(co_p, -1)), F(bp)
             for i, c in enumerate(self.topo.input_chans):
                 p = f"zero_convs.{i}.0"
                 self.w[p + ".w"], self.w[p + ".b"] = H(sd[p + ".weight"].reshape(c, c)), F(sd[p + ".bias"])
@@ -177,14 +190,32 @@ class PackedNet:
         o = self.ops
         B, C, Hh, Wh = hint_nchw.shape
         x = hint_nchw.permute(0, 2, 3, 1).contiguous().to(self.hdt)
+        n = len(HINT_STRIDES)
+        tc = os.environ.get("EA_HINT_TC", "1") != "0" and Hh % 8 == 0 and Wh % 8 == 0
         cin = C
         for i, s in enumerate(HINT_STRIDES):
             p = f"input_hint_block.{2 * i}"
             cout = self.w[p + ".w"].shape[-1]
             Ho, Wo = (Hh + s - 1) // s, (Wh + s - 1) // s
-            y = torch.empty(B, Ho, Wo, cout, device=self.dev, dtype=self.hdt)
-            o.conv_direct(x, self.w[p + ".w"], self.w[p + ".b"], y, B=B, Hin=Hh, Win=Wh, Cin=cin, Cout=cout,
-                          ksize=3, stride=s, silu=(i != len(HINT_STRIDES) - 1))
+            if not tc:
+                y = torch.empty(B, Ho, Wo, cout, device=self.dev, dtype=self.hdt)
+                o.conv_direct(x, self.w[p + ".w"], self.w[p + ".b"], y, B=B, Hin=Hh, Win=Wh, Cin=cin, Cout=cout,
+                              ksize=3, stride=s, silu=(i != n - 1))
+            elif i == 0:
+                # first layer (3 input channels, un-normalised 0..255 id map: fp32 weights) on the direct kernel,
+                # written into a buffer whose channels are padded to 64 for the tensor-core layers that follow
+                cp = -(-cout // 64) * 64
+                y = torch.zeros(B, Ho, Wo, cp, device=self.dev, dtype=self.hdt)
+                o.conv_direct(x, self.w[p + ".w"], self.w[p + ".b"], y, B=B, Hin=Hh, Win=Wh, Cin=cin, Cout=cout,
+                              ksize=3, stride=s, silu=True, ldo=cp)
+            else:
+                # layers 2..8 as implicit-GEMM convolutions on the tensor cores (1.5 GFLOP per image on CUDA cores
+                # cost several ms per request; padded to 64-channel multiples they are ~64 GFLOP of tcgen05 work)
+                wp = self.w[p + ".wp"]
+                y = torch.empty(B, Ho, Wo, wp.shape[0], device=self.dev, dtype=self.hdt)
+                o.gemm(x, wp, y.view(B * Ho * Wo, -1), mode=L.EA_GEMM_CONV_S1 if s == 1 else L.EA_GEMM_CONV_S2,
+                       conv=(B, Ho, Wo, x.shape[-1]), bias=self.w[p + ".bp"],
+                       act=L.EA_ACT_SILU if i != n - 1 else L.EA_ACT_NONE)
             x, cin, Hh, Wh = y, cout, Ho, Wo
         return x
 

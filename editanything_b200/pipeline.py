@@ -452,7 +452,7 @@ class StableDiffusionControlNetInpaintPipeline:
 
         eng = self.engine
         dev = eng.dev
-        eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale, guess_mode=guess_mode)
+        eng.prepare(prompt_embeds, conds, controlnet_conditioning_scale, guess_mode=guess_mode, cfg_duplicated=do_cfg)
         # fused step: the built-in DDIM, and UniPC (what every reference entry point installs, editany_lora.py:383,418)
         # through its per-step coefficient rows; any other scheduler object runs eng.eps + scheduler.step
         unipc = isinstance(self.scheduler, UniPCMultistepScheduler) and self.scheduler.config.solver_order <= 2

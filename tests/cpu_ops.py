@@ -152,7 +152,10 @@ def conv_direct(x, w, bias, out, *, B, Hin, Win, Cin, Cout, ksize=3, stride=1, s
     y = y.permute(0, 2, 3, 1)
     if add is not None:
         y = y + add.float().reshape(y.shape)
-    out.copy_(y.reshape(out.shape))
+    if ldo and ldo != Cout:          # output pixel stride > Cout: only the first Cout channels of every pixel are written
+        out.reshape(-1, ldo)[:, :Cout].copy_(y.reshape(-1, Cout))
+    else:
+        out.copy_(y.reshape(out.shape))
     return out
 
 
