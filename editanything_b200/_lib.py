@@ -67,6 +67,7 @@ SYMBOLS = {
     "ea_dtype_name": (C.c_char_p, []),
     "ea_strerror": (C.c_char_p, [_I]),
     "ea_init": (_I, []),
+    "ea_last_error": (C.c_char_p, []),
     "ea_launch_count": (_L, []),
     "ea_reset_launch_count": (None, []),
     "ea_set_pdl": (None, [_I]),
@@ -127,4 +128,6 @@ def lib():
 
 def check(status, what=""):
     if status != 0:
-        raise RuntimeError(f"libea_b200 {what} failed: {load().ea_strerror(status).decode()} ({status})")
+        detail = load().ea_last_error().decode() if status == -4 else ""
+        raise RuntimeError(f"libea_b200 {what} failed: {load().ea_strerror(status).decode()} ({status})" +
+                           (f" [{detail}]" if detail else ""))

@@ -1,5 +1,6 @@
 // ea_api.cu — library bookkeeping for the C ABI declared in include/editanything_b200.h.
 #include <atomic>
+#include <stdio.h>
 #include <stdlib.h>
 #include "ea_common.cuh"
 #include "ea_internal.h"
@@ -39,6 +40,13 @@ int ea_pdl_enabled() {
 extern "C" void ea_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 void ea_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static char g_last_error[256] = "";
+int ea_cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+  return EA_ERR_CUDA;
+}
+extern "C" const char* ea_last_error(void) { return g_last_error; }
 
 int ea_sm_count() {
   static int n_sm[EA_MAX_DEV] = {0};

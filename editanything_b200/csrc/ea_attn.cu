@@ -73,6 +73,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error
+// 1.14e-4 - below the 4.9e-4 rounding of the 16-bit P it feeds).  The long self-attention layers are bound by the
+// exp unit (16 MUFU lanes per SM: XU pipe 65 % busy, tensor pipe 21 %, profiles/r02c_misc_ncu_full.txt) while the FMA
+// pipe idles; computing every fourth probability here takes a quarter of the load off the MUFU.  x <= 0; masked keys
+// (x = -inf) clamp to 2^-126 ~ 0.  -DEA_ATTN_EXP_MUFU_ONLY switches it off (A/B).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float xf = x + 12582912.f;               // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float r = x - (xf - 12582912.f);         // fractional part in [-0.5, 0.5]
+  float p = fmaf(0.05459282547f, r, 0.24221783876f);
+  p = fmaf(p, r, 0.69336861372f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+
 __device__ __forceinline__ void tmem_st16_half(uint32_t taddr, const uint32_t (&r)[16]) {
   tmem_st16(taddr, r);
 }
@@ -685,7 +700,11 @@ ea_attn_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const float e0 = ex2_approx(fmaf(__uint_as_float(v[h][i]), p.scale_log2, neg_m));
           const float e1 = ex2_approx(fmaf(__uint_as_float(v[h][i + 1]), p.scale_log2, neg_m));
           const float e2 = ex2_approx(fmaf(__uint_as_float(v[h][i + 2]), p.scale_log2, neg_m));
+#ifdef EA_ATTN_EXP_MUFU_ONLY
           const float e3 = ex2_approx(fmaf(__uint_as_float(v[h][i + 3]), p.scale_log2, neg_m));
+#else
+          const float e3 = ex2_poly(fmaf(__uint_as_float(v[h][i + 3]), p.scale_log2, neg_m));
+#endif
           s0 += e0; s1 += e1; s2 += e2; s3 += e3;
           pk[i >> 1] = ea_pack2(e0, e1);
           pk[(i >> 1) + 1] = ea_pack2(e2, e3);

@@ -1033,7 +1033,7 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 template <int EPI_WG, int NG>
 // 320 threads x 200 registers = 64000 of the SM's 65536: ptxas, left alone with __launch_bounds__(320, 1), stopped at
 // 168 and spilled the double-buffered TMEM drain (va / vb) to local memory inside the epilogue loop
-__global__ void __launch_bounds__(64 + 128 * EPI_WG) __maxnreg__(EPI_WG == 2 ? 200 : 255)
+__global__ void __launch_bounds__(64 + 128 * EPI_WG, 1)
 ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int tiles_per_group, const int m_tiles,
                           const int n_groups) {
   // the tile list runs over (group, tile): every group has the same shape and plan; `p` below = the shared fields
@@ -1694,7 +1694,8 @@ static bool gemm_same_problem(const ea_gemm_args* a, const ea_gemm_args* b) {
 template <typename K>
 static int set_max_smem(K kernel, int bytes, int& cached) {
   if (bytes > cached) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return EA_ERR_CUDA;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return ea_cuda_fail(e, "ea_gemm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     cached = bytes;
   }
   return EA_OK;
@@ -1858,7 +1859,9 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
       }
     }
     ea_count_launch();
-    return (lp == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
+    if (lp != cudaSuccess) return ea_cuda_fail(lp, "ea_gemm: persistent kernel launch");
+    const cudaError_t pe = cudaGetLastError();
+    return pe == cudaSuccess ? 0 : ea_cuda_fail(pe, "ea_gemm: after the persistent kernel launch");
   }
   if (plan.splits > 1 && !a->no_spin) {
     // the spinning fix-up makes split CTAs wait for their siblings: every CTA of the grid must be
@@ -1893,7 +1896,9 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
     }
   }
   ea_count_launch();
-  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : EA_ERR_CUDA;
+  if (le != cudaSuccess) return ea_cuda_fail(le, "ea_gemm: kernel launch");
+  const cudaError_t ke = cudaGetLastError();
+  return ke == cudaSuccess ? 0 : ea_cuda_fail(ke, "ea_gemm: after the kernel launch");
 }
 
 extern "C" int ea_gemm(const ea_gemm_args* a, void* stream) { return ea_gemm_grouped(a, 1, stream); }

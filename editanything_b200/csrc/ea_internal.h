@@ -21,6 +21,8 @@ static inline int ea_dev() {
   return d < EA_MAX_DEV ? d : EA_MAX_DEV - 1;
 }
 int ea_sm_count();   // SMs of the current device (cached per device)
+// Remembers the CUDA error behind an EA_ERR_CUDA status (ea_last_error() returns it); returns EA_ERR_CUDA.
+int ea_cuda_fail(cudaError_t e, const char* where);
 
 // Programmatic dependent launch (PDL): every kernel of this library calls griddepcontrol.wait before
 // it touches global memory, so consecutive launches on a stream may overlap the next kernel's

@@ -41,6 +41,8 @@ enum ea_act { EA_ACT_NONE = 0, EA_ACT_SILU = 1, EA_ACT_GELU = 2, EA_ACT_GEGLU = 
 int ea_version(void);
 const char* ea_dtype_name(void);      /* "float16" | "bfloat16" */
 const char* ea_strerror(int status);
+/* The CUDA error (name, message, call site) behind the most recent EA_ERR_CUDA status of ea_gemm; "" if none. */
+const char* ea_last_error(void);
 int ea_init(void);                    /* resolves cuTensorMapEncodeTiled; 0 on success */
 long long ea_launch_count(void);      /* kernels launched by this library since reset */
 void ea_set_pdl(int on);              /* programmatic dependent launch between consecutive kernels
