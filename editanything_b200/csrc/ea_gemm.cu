@@ -1030,10 +1030,20 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // second warp-group takes every other 64-column group of the accumulator.  The one-warp-per-sub-partition
 // epilogue is instruction-latency bound (3-5 us per tile, profiles/r01p_exp_step_chain_gemm_in_context.txt);
 // a second warp on the same scheduler hides it, also for grids of a single wave.
+// Registers (EPI_WG = 2): an SM sub-partition holds 16384 registers = 512 per lane.  Ten warps put three on some
+// sub-partition, which caps every thread at 168 (a launch at 200 is refused: cudaErrorLaunchOutOfResources, round 2
+// session 6) and spilled the double-buffered TMEM drain.  So the block is THREE full warp-groups - epilogue warps
+// 0-7, control warp-group 8-11 (TMA, MMA, two idle warps) - launched at 168 registers, and `setmaxnreg` moves the
+// budget: control warps shrink to 48, epilogue warps grow to 232 (2 x 232 + 48 = 512).
+#ifndef EA_PREG_CTRL
+#define EA_PREG_CTRL 48
+#define EA_PREG_EPI 232
+#endif
+template <int EPI_WG> struct PersistShape {
+  static constexpr int kThreads = EPI_WG == 2 ? 384 : 192;
+};
 template <int EPI_WG, int NG>
-// 320 threads x 200 registers = 64000 of the SM's 65536: ptxas, left alone with __launch_bounds__(320, 1), stopped at
-// 168 and spilled the double-buffered TMEM drain (va / vb) to local memory inside the epilogue loop
-__global__ void __launch_bounds__(64 + 128 * EPI_WG, 1)
+__global__ void __launch_bounds__(PersistShape<EPI_WG>::kThreads, 1)
 ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int tiles_per_group, const int m_tiles,
                           const int n_groups) {
   // the tile list runs over (group, tile): every group has the same shape and plan; `p` below = the shared fields
@@ -1098,8 +1108,10 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // no code is shared between the two register budgets after this point: each role branch changes its own
+  if (warp >= EPI_WARPS) {
+  if (EPI_WG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EA_PREG_CTRL));
   pdl_wait();
-
   if (warp == PW_TMA) {
     // ============================ TMA producer ============================
     if (lane == 0) {
@@ -1194,8 +1206,11 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       abuf ^= 1;
       if (abuf == 0) aphase ^= 1u;
     }
+  }
   } else {
     // ============================== epilogue ==============================
+    if (EPI_WG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EA_PREG_EPI));
+    pdl_wait();
     const int wq = warp & 3;             // TMEM lane quarter = warp id mod 4
     const int wg = warp >> 2;            // epilogue warp-group: owns the 64-column groups gi with gi % EPI_WG == wg
     const int r = wq * 32 + lane;
@@ -1840,21 +1855,21 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
     if (persist_wg == 2) {
       if (G == 1) {
         if ((rc = set_max_smem(ea_gemm_persistent_kernel<2, 1>, smem_bytes, cache_p[2][0]))) return rc;
-        lp = ea_launch(ea_gemm_persistent_kernel<2, 1>, dim3((unsigned)grid_p), dim3(64 + 128 * 2), (size_t)smem_bytes,
+        lp = ea_launch(ea_gemm_persistent_kernel<2, 1>, dim3((unsigned)grid_p), dim3(PersistShape<2>::kThreads), (size_t)smem_bytes,
                        stream, L1, (int)tiles, m_tiles, G);
       } else {
         if ((rc = set_max_smem(ea_gemm_persistent_kernel<2, GEMM_MAX_GROUPS>, smem_bytes, cache_p[2][1]))) return rc;
-        lp = ea_launch(ea_gemm_persistent_kernel<2, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(64 + 128 * 2),
+        lp = ea_launch(ea_gemm_persistent_kernel<2, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(PersistShape<2>::kThreads),
                        (size_t)smem_bytes, stream, L, (int)tiles, m_tiles, G);
       }
     } else {
       if (G == 1) {
         if ((rc = set_max_smem(ea_gemm_persistent_kernel<1, 1>, smem_bytes, cache_p[1][0]))) return rc;
-        lp = ea_launch(ea_gemm_persistent_kernel<1, 1>, dim3((unsigned)grid_p), dim3(64 + 128), (size_t)smem_bytes,
+        lp = ea_launch(ea_gemm_persistent_kernel<1, 1>, dim3((unsigned)grid_p), dim3(PersistShape<1>::kThreads), (size_t)smem_bytes,
                        stream, L1, (int)tiles, m_tiles, G);
       } else {
         if ((rc = set_max_smem(ea_gemm_persistent_kernel<1, GEMM_MAX_GROUPS>, smem_bytes, cache_p[1][1]))) return rc;
-        lp = ea_launch(ea_gemm_persistent_kernel<1, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(64 + 128),
+        lp = ea_launch(ea_gemm_persistent_kernel<1, GEMM_MAX_GROUPS>, dim3((unsigned)grid_p), dim3(PersistShape<1>::kThreads),
                        (size_t)smem_bytes, stream, L, (int)tiles, m_tiles, G);
       }
     }
