@@ -194,6 +194,28 @@ __device__ __forceinline__ void stage_flush(const uint4* stg, int lane, ea_half*
   // instructions a linear GEMM executed (profiles/r02c_gemm_ncu_source_hot.txt).
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = col0 + piece * 8;
+#ifdef EA_EPI_FLUSH_ROLLED   // A/B: the compact rolled form (fewer instruction-cache lines, more instructions executed)
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + rsub;
+    long long m_r;
+    int ok_r;
+    if (lin_m0 >= 0) {
+      m_r = lin_m0 + row;
+      ok_r = m_r < M;
+    } else {
+      m_r = __shfl_sync(0xffffffffu, m_mine, row);
+      ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
+    }
+    if (ok_r && piece < pieces && col < n_limit) {
+      const uint4 val = stg[row * 8 + (piece ^ (row & 7))];
+      *reinterpret_cast<uint4*>(out + m_r * ldo + col) = val;
+      if (out2) *reinterpret_cast<uint4*>(out2 + m_r * ldo2 + col) = val;
+    }
+  }
+  __syncwarp();
+  return;
+#endif
   const bool col_ok = piece < pieces && col < n_limit;
   uint4 val[8];
 #pragma unroll
@@ -1034,14 +1056,25 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 // sub-partition, which caps every thread at 168 (a launch at 200 is refused: cudaErrorLaunchOutOfResources, round 2
 // session 6) and spilled the double-buffered TMEM drain.  So the block is THREE full warp-groups - epilogue warps
 // 0-7, control warp-group 8-11 (TMA, MMA, two idle warps) - launched at 168 registers, and `setmaxnreg` moves the
-// budget: control warps shrink to 48, epilogue warps grow to 232 (2 x 232 + 48 = 512).
+// budget: control warps shrink to 40, epilogue warps grow to 232 (2 x 232 + 40 = 3 x 168, the launch allocation).
+// The pool setmaxnreg draws from is what the LAUNCH allocated (384 x 168), not the whole file: control + 2 x epilogue
+// <= 3 x 168 = 504 per lane.  48 / 232 asked for 1024 registers the pool never had: launch failure / hang (session 8).
 #ifndef EA_PREG_CTRL
-#define EA_PREG_CTRL 48
+#define EA_PREG_CTRL 40
 #define EA_PREG_EPI 232
 #endif
+static_assert(EA_PREG_CTRL + 2 * EA_PREG_EPI <= 504, "setmaxnreg budget exceeds the launch allocation");
+#ifdef EA_PERSIST_LEGACY_LAYOUT   // A/B: 320 threads, 168 registers for every warp
+template <int EPI_WG> struct PersistShape {
+  static constexpr int kThreads = 64 + 128 * EPI_WG;
+  static constexpr bool kSetMaxNReg = false;
+};
+#else
 template <int EPI_WG> struct PersistShape {
   static constexpr int kThreads = EPI_WG == 2 ? 384 : 192;
+  static constexpr bool kSetMaxNReg = EPI_WG == 2;
 };
+#endif
 template <int EPI_WG, int NG>
 __global__ void __launch_bounds__(PersistShape<EPI_WG>::kThreads, 1)
 ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int tiles_per_group, const int m_tiles,
@@ -1110,7 +1143,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   const uint32_t tmem_base = *tmem_slot;
   // no code is shared between the two register budgets after this point: each role branch changes its own
   if (warp >= EPI_WARPS) {
-  if (EPI_WG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EA_PREG_CTRL));
+  if (PersistShape<EPI_WG>::kSetMaxNReg) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(EA_PREG_CTRL));
   pdl_wait();
   if (warp == PW_TMA) {
     // ============================ TMA producer ============================
@@ -1209,7 +1242,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   }
   } else {
     // ============================== epilogue ==============================
-    if (EPI_WG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EA_PREG_EPI));
+    if (PersistShape<EPI_WG>::kSetMaxNReg) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EA_PREG_EPI));
     pdl_wait();
     const int wq = warp & 3;             // TMEM lane quarter = warp id mod 4
     const int wg = warp >> 2;            // epilogue warp-group: owns the 64-column groups gi with gi % EPI_WG == wg
@@ -1342,6 +1375,18 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
         };
         uint32_t va[32], vb[32];
         int c = wg * 64;
+#ifdef EA_EPI_NO_PINGPONG   // A/B: one copy of the chunk body, 32 register moves per chunk
+        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, vb);
+        while (c < p.BN) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = vb[j];
+          const int nc = next_chunk(c);
+          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
+          process(va, c);
+          c = nc;
+        }
+#else
         if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, va);
         while (c < p.BN) {
           tmem_ld_wait();
@@ -1356,6 +1401,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
           process(vb, c);
           c = nc;
         }
+#endif
       } else if (EPI_WG == 1) {
         for (int c = 0; c < half_bn; c += 32) {
           uint32_t xv[32], gv[32];
