@@ -194,28 +194,6 @@ __device__ __forceinline__ void stage_flush(const uint4* stg, int lane, ea_half*
   // instructions a linear GEMM executed (profiles/r02c_gemm_ncu_source_hot.txt).
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = col0 + piece * 8;
-#ifdef EA_EPI_FLUSH_ROLLED   // A/B: the compact rolled form (fewer instruction-cache lines, more instructions executed)
-#pragma unroll 1
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + rsub;
-    long long m_r;
-    int ok_r;
-    if (lin_m0 >= 0) {
-      m_r = lin_m0 + row;
-      ok_r = m_r < M;
-    } else {
-      m_r = __shfl_sync(0xffffffffu, m_mine, row);
-      ok_r = __shfl_sync(0xffffffffu, (int)ok_mine, row);
-    }
-    if (ok_r && piece < pieces && col < n_limit) {
-      const uint4 val = stg[row * 8 + (piece ^ (row & 7))];
-      *reinterpret_cast<uint4*>(out + m_r * ldo + col) = val;
-      if (out2) *reinterpret_cast<uint4*>(out2 + m_r * ldo2 + col) = val;
-    }
-  }
-  __syncwarp();
-  return;
-#endif
   const bool col_ok = piece < pieces && col < n_limit;
   uint4 val[8];
 #pragma unroll
@@ -1297,8 +1275,10 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       if (!geglu) {
         const float* cbr = cbt + ((!ln && ri.batch != b_first) ? 256 : 0);
         // this warp-group's chunks: both halves of the 64-column groups wg, wg + EPI_WG, ...; the next chunk's
-        // tcgen05.ld is in flight while the current one is converted and stored.  The two register buffers are
-        // used alternately (ping-pong) instead of moving 32 registers per chunk.
+        // tcgen05.ld is in flight while the current one is converted and stored.  ONE copy of the chunk body on
+        // purpose (32 register moves per chunk): alternating two register buffers needs two copies of the ~1500
+        // instruction body, which no longer fit the 32 KB L1.5 instruction cache - measured +0.25 ms per step
+        // (profiles/r02e_ab_epilogue.txt).
         auto next_chunk = [&](int c) { return ((c & 32) == 0 && c + 32 < p.BN) ? c + 32 : (c & ~63) + GSTEP; };
         auto process = [&](const uint32_t (&v)[32], const int c) {
           const int n_first = ncol0 + c;
@@ -1375,7 +1355,6 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
         };
         uint32_t va[32], vb[32];
         int c = wg * 64;
-#ifdef EA_EPI_NO_PINGPONG   // A/B: one copy of the chunk body, 32 register moves per chunk
         if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, vb);
         while (c < p.BN) {
           tmem_ld_wait();
@@ -1386,22 +1365,6 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
           process(va, c);
           c = nc;
         }
-#else
-        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, va);
-        while (c < p.BN) {
-          tmem_ld_wait();
-          int nc = next_chunk(c);
-          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
-          process(va, c);
-          c = nc;
-          if (c >= p.BN) break;
-          tmem_ld_wait();
-          nc = next_chunk(c);
-          if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, va);
-          process(vb, c);
-          c = nc;
-        }
-#endif
       } else if (EPI_WG == 1) {
         for (int c = 0; c < half_bn; c += 32) {
           uint32_t xv[32], gv[32];
