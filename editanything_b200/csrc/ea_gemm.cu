@@ -150,17 +150,16 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // The loads of a batch of 16 partials are all issued before the first add - a plain loop compiled to one dependent L2
 // round trip per partial (10 for C = 320, 40 for C = 1280: 22 % of all stall samples of the GEGLU launch,
 // profiles/r02c_gemm_ncu_source_hot.txt).  The adds keep their fixed order, so the result stays deterministic.
-template <int W = 16>   // loads in flight per batch (the 40-register side warps of the persistent kernel use 8)
 __device__ __forceinline__ void ln_row_stats(const GemmKParams& p, long long m, float& ln_r, float& ln_nm) {
   float s = 0.f, q = 0.f;
   const float2* base = p.ln_stats + m;
-  for (int j0 = 0; j0 < p.ln_parts; j0 += W) {
-    float2 v[W];
+  for (int j0 = 0; j0 < p.ln_parts; j0 += 16) {
+    float2 v[16];
 #pragma unroll
-    for (int u = 0; u < W; ++u)
+    for (int u = 0; u < 16; ++u)
       v[u] = (j0 + u < p.ln_parts) ? __ldcg(base + (size_t)(j0 + u) * p.M) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < W; ++u) {
+    for (int u = 0; u < 16; ++u) {
       s += v[u].x;
       q += v[u].y;
     }
@@ -1019,44 +1018,6 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
   bn = 128 / (bw * bh);
 }
 
-// Per-tile side data of the persistent kernel: the column vectors the epilogue adds (bias, time-embedding row vectors
-// of the tile's first / last image, or the LayerNorm-fold g vector) into cbt[0..255] / cbt[256..511], and for a
-// LayerNorm-folded GEMM every row's (rstd, -mean * rstd) into lnrow[0..127].  `tid` of `nthreads` cooperate.
-__device__ __forceinline__ void persist_side_fill(const GemmKParams& p, int tm, int tn, float* cbt, float2* lnrow,
-                                                  int tid, int nthreads) {
-  const int ncol0 = tn * p.BN;
-  const bool ln = p.ln_stats != nullptr;
-  if (p.act != EA_ACT_GEGLU) {
-    const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
-    for (int i = tid; i < p.BN; i += nthreads) {
-      const int col = ncol0 + i;
-      float v0 = 0.f, v1 = 0.f;
-      if (col < p.N) {
-        const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
-        v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
-        v1 = ln ? __ldg(p.ln_g + col)
-                : bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
-      }
-      cbt[i] = v0;
-      cbt[256 + i] = v1;
-    }
-  } else {
-    for (int i = tid; i < p.BN; i += nthreads) {
-      const bool in = ncol0 + i < p.N;
-      cbt[i] = (p.bias && in) ? __ldg(p.bias + ncol0 + i) : 0.f;
-      if (ln) cbt[256 + i] = in ? __ldg(p.ln_g + ncol0 + i) : 0.f;
-    }
-  }
-  if (ln && lnrow) {
-    for (int r = tid; r < BM; r += nthreads) {
-      const RowInfo ri = row_info(p, tm, r);
-      float a = 1.f, b = 0.f;
-      if (ri.ok) ln_row_stats<8>(p, ri.m, a, b);
-      lnrow[r] = make_float2(a, b);
-    }
-  }
-}
-
 // ---- persistent variant ---------------------------------------------------------------------------
 // EXPERIMENTAL (off unless ea_gemm_args.force_persistent = 1 or EA_GEMM_PERSIST=1; not yet validated on
 // hardware - DESIGN.md section 8, item 1).  One CTA per SM walks the tile list (tile -> (tm, tn) with tm
@@ -1121,15 +1082,9 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;      // [2] accumulator complete
   uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (one arrival per epilogue warp)
-  uint64_t* side_bar = tempty_bar + 2;             // [2] per-tile side data ready (SIDE layout: one arrival per side warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* cb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) &
                                        ~uintptr_t(15));   // [2 tile parities][2][256]
-  float2* lnrow = reinterpret_cast<float2*>(cb + 2 * 512);   // [2 tile parities][128 rows] (rstd, -mean * rstd)
-  // SIDE: the two spare warps of the control warp-group prepare every tile's side data (bias / LayerNorm-fold column
-  // vectors, the rows' LayerNorm statistics) one tile ahead, so that the epilogue warps never wait on those global
-  // loads: their chain per tile was loads -> reduce -> loads -> smem -> barrier -> TMEM drain, all serial.
-  constexpr bool SIDE = PersistShape<EPI_WG>::kSetMaxNReg;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -1156,7 +1111,6 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], EPI_WARPS);
-      mbar_init(&side_bar[b], 2);
     }
     fence_mbar_init();
   }
@@ -1263,21 +1217,6 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       abuf ^= 1;
       if (abuf == 0) aphase ^= 1u;
     }
-  } else if (SIDE) {
-    // ============================ side data (2 warps) =====================
-    const int st = threadIdx.x - (PW_MMA + 1) * 32;   // 0 .. 63
-    int abuf = 0, it = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      EA_PERSIST_TILE_GROUP()
-      // buffer `abuf` was last read by the epilogue of tile it - 2: free once that accumulator was handed back
-      mbar_wait(&tempty_bar[abuf], aphase ^ 1u);
-      persist_side_fill(p, tm, tn, cb + abuf * 512, lnrow + abuf * 128, st, 64);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&side_bar[abuf]);
-      abuf ^= 1;
-      if (abuf == 0) aphase ^= 1u;
-    }
   }
   } else {
     // ============================== epilogue ==============================
@@ -1301,25 +1240,35 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       const int ncol0 = tn * p.BN;
       float* cbt = cb + (it & 1) * 512;
       const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
-      const int b_first = row_info(p, tm, 0).batch;
+      const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
       uint4 rres[8];
       // LayerNorm fold, consumer side (see ea_gemm_kernel)
       const bool ln = p.ln_stats != nullptr;
       float ln_r = 1.f, ln_nm = 0.f;
-      if (!geglu && has_res && wg * 64 < p.BN)
-        residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
-      if (SIDE) {
-        mbar_wait(&side_bar[abuf], fphase);
-        if (ln) {
-          const float2 t = lnrow[abuf * 128 + r];
-          ln_r = t.x;
-          ln_nm = t.y;
+      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
+      if (!geglu) {
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
+          const int col = ncol0 + i;
+          float v0 = 0.f, v1 = 0.f;
+          if (col < p.N) {
+            const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
+            v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
+            v1 = ln ? __ldg(p.ln_g + col)
+                    : bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
+          }
+          cbt[i] = v0;
+          cbt[256 + i] = v1;
         }
+        if (has_res && wg * 64 < p.BN)
+          residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
       } else {
-        if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
-        persist_side_fill(p, tm, tn, cbt, nullptr, et, EPI_THREADS);
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
+          const bool in = ncol0 + i < p.N;
+          cbt[i] = (p.bias && in) ? __ldg(p.bias + ncol0 + i) : 0.f;
+          if (ln) cbt[256 + i] = in ? __ldg(p.ln_g + ncol0 + i) : 0.f;
+        }
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[abuf], fphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)abuf * acc_cols;
@@ -1866,7 +1815,7 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
   int stages = 0, smem_bytes = 0, pair_release = 0;
   if (persist_launch) {
     const int sbp = BM * BK * 2 + BN * BK * 2;
-    const int fixed = 32768 * persist_wg + (2 * 8 + 6) * 8 + 32 + 2 * 2 * 256 * 4 + 2 * 128 * 8 + 1024;   // staging, barriers, slot, column vectors, row stats, align
+    const int fixed = 32768 * persist_wg + (2 * 8 + 4) * 8 + 32 + 2 * 2 * 256 * 4 + 1024;   // staging, barriers, slot, bias, align
     stages = (224 * 1024 - fixed) / sbp;
     if (stages > 8) stages = 8;
     if (a->force_stages > 0 && a->force_stages < stages) stages = a->force_stages;

@@ -1,7 +1,10 @@
 """Per-shape sweep of the step's small-K linears (3 networks grouped like the lockstep encoder): tile width, kernel
 flavour (one-tile kernel / CTA pairs / 8-warp persistent) -> us and TFLOP/s.  Dev tool (GPU box)."""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 
 import torch
 
