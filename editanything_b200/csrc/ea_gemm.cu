@@ -1061,12 +1061,22 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   // (group 0), each tile re-binds `p` / the tensor maps to its own group
   const GemmKParams& p = L.g[0].p;
   const int num_tiles = tiles_per_group * (NG == 1 ? 1 : n_groups);
+  // Tile order.  Default: a CTA takes tiles blockIdx.x, + gridDim.x, ... with tm fastest (CTAs working side by side
+  // share their weight tile in L2).  LayerNorm-folded GEMMs: a CTA takes a CONTIGUOUS run of tiles with tn fastest, so
+  // consecutive tiles belong to the same rows and their LayerNorm statistics are reduced once per row block instead of
+  // once per tile (the per-tile reduction cost 6-21 us per launch, profiles/r02f_ln_consumer_cost.txt).
+  const bool row_major = p.ln_stats != nullptr;
+  const int n_tiles = tiles_per_group / m_tiles;
+  const int t_begin = row_major ? (int)((long long)blockIdx.x * num_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_end = row_major ? (int)((long long)(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
+  const int t_step = row_major ? 1 : (int)gridDim.x;
 #define EA_PERSIST_TILE_GROUP()                                                    \
   const int gi = NG == 1 ? 0 : tile / tiles_per_group;                             \
   const int gtile = NG == 1 ? tile : tile - gi * tiles_per_group;                  \
   const GemmGroup& GG = L.g[gi];                                                   \
   const GemmKParams& p = GG.p;                                                     \
-  const int tm = gtile % m_tiles, tn = gtile / m_tiles;
+  const int tm = row_major ? gtile / n_tiles : gtile % m_tiles;                    \
+  const int tn = row_major ? gtile - tm * n_tiles : gtile / m_tiles;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -1093,7 +1103,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   const uint32_t acc_cols = tmem_cols_for(p.BN);
 
   if (warp == PW_TMA && lane == 0) {
-    const int g0 = NG == 1 ? 0 : min((int)blockIdx.x / tiles_per_group, n_groups - 1);
+    const int g0 = NG == 1 ? 0 : min(t_begin / tiles_per_group, n_groups - 1);
     tma_prefetch_desc(&L.g[g0].tmA0);
     tma_prefetch_desc(&L.g[g0].tmB);
     if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
@@ -1130,7 +1140,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       uint32_t phase = 0;
       uint8_t* sa = smem;
       const int cin = p.cin_blocks * BK;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         EA_PERSIST_TILE_GROUP()
         const CUtensorMap& tmA0 = GG.tmA0;
         const CUtensorMap& tmA1 = GG.tmA1;
@@ -1191,7 +1201,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     uint32_t phase = 0;
     int abuf = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
       mbar_wait(&tempty_bar[abuf], aphase ^ 1u);      // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t td = tb + (uint32_t)abuf * acc_cols;
@@ -1233,7 +1243,9 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     constexpr int GSTEP = 64 * EPI_WG;   // column distance between two groups of one warp-group
     int abuf = 0, it = 0;
     uint32_t fphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int ln_unit = -1;
+    float ln_r = 1.f, ln_nm = 0.f;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       EA_PERSIST_TILE_GROUP()
       const bool has_res = p.residual != nullptr;
       const RowInfo ri = row_info(p, tm, r);
@@ -1244,8 +1256,12 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       uint4 rres[8];
       // LayerNorm fold, consumer side (see ea_gemm_kernel)
       const bool ln = p.ln_stats != nullptr;
-      float ln_r = 1.f, ln_nm = 0.f;
-      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
+      if (ln && ln_unit != gi * m_tiles + tm) {   // row_major order: the same rows for n_tiles tiles in a row
+        ln_unit = gi * m_tiles + tm;
+        ln_r = 1.f;
+        ln_nm = 0.f;
+        if (ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
+      }
       if (!geglu) {
         for (int i = et; i < p.BN; i += EPI_THREADS) {
           const int col = ncol0 + i;
@@ -1454,7 +1470,11 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
   GemmPlan best = {0, 0, 1, nkb, 1, 1e30, 0};
   // CTA pairs (cta_group::2): per SM the TMA stream per K-block shrinks from 16 KB + BN*128 B to
   // 16 KB + BN*64 B for the same 128 x BN MACs.  Only without split-K and for stride-1 shapes.
-  if (allow_two && mt >= 2) {
+  // 64x64-level projections (M = 8192, N = K = 320: attention out / proj_out with residual): the model picks 96,
+  // the per-shape sweep (profiles/r02f_gemm_shape_sweep.txt) has 128 26 % faster.  EA_PL_N320_BN overrides for A/B.
+  static const int pl_n320_bn = (int)pl_env("EA_PL_N320_BN", 128.0);
+  const int pin_bn = (mt == 64 && N == 320 && nkb == 5 && act != EA_ACT_GEGLU) ? pl_n320_bn : 0;
+  if (allow_two && mt >= 2 && pin_bn == 0) {
     for (int BN = 256; BN >= 64; BN -= 32) {
       if (act == EA_ACT_GEGLU && BN != 128) continue;
       if (N <= BN - 32) continue;
@@ -1492,6 +1512,7 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
   for (int BN = 256; BN >= 32; BN -= 32) {
     if (act == EA_ACT_GEGLU && BN != 128) continue;  // weights are interleaved per 128-row block
     if (BN > 32 && N <= BN - 32) continue;            // a narrower tile covers N just as well
+    if (pin_bn > 0 && BN != pin_bn) continue;
     const int nt = (N + BN - 1) / BN;
     const long long tiles = (long long)mt * nt * groups;
     const int stage_bytes = BM * BK * 2 + BN * BK * 2;
