@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("force_persistent", C.c_int),
         ("rowstats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_g", C.c_void_p), ("ln_parts", C.c_int),
         ("ln_eps", C.c_float), ("row_scale", C.c_void_p),
+        ("prefetch", C.c_void_p * 3), ("prefetch_bytes", C.c_longlong * 3),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
     ]
 

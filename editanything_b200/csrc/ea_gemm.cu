@@ -75,6 +75,9 @@ struct GemmKParams {
   int ln_parts;
   float ln_inv_c, ln_eps;
   const float* row_scale;   // [M] fp32 per-row output factor (general / split-K epilogues only) or null
+  const char* pf[EA_GEMM_MAX_PREFETCH];   // L2 prefetch hints (a later launch's weights) or null; pf_ctas CTAs share each range
+  long long pf_bytes[EA_GEMM_MAX_PREFETCH];
+  int pf_ctas;
   int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
@@ -150,6 +153,27 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // The loads of a batch of 16 partials are all issued before the first add - a plain loop compiled to one dependent L2
 // round trip per partial (10 for C = 320, 40 for C = 1280: 22 % of all stall samples of the GEGLU launch,
 // profiles/r02c_gemm_ncu_source_hot.txt).  The adds keep their fixed order, so the result stays deterministic.
+// L2 prefetch of a later launch's weights (ea_gemm_args.prefetch): lanes `lane0 .. 31` of one warp in each of the first
+// pf_ctas CTAs walk the range in 8 KB pieces.  Issued before the dependency wait - weights are never produced by a
+// predecessor kernel - so HBM works on the next layer while this one computes from L2.
+__device__ __forceinline__ void l2_prefetch_hint(const GemmKParams& p, int cta, int lane, int lane0) {
+  if (cta >= p.pf_ctas || lane < lane0) return;
+  constexpr long long CH = 8192;
+  const int nl = 32 - lane0;
+#pragma unroll 1
+  for (int i = 0; i < EA_GEMM_MAX_PREFETCH; ++i) {
+    if (p.pf[i] == nullptr) continue;
+    const long long nchunks = (p.pf_bytes[i] + CH - 1) / CH;
+    for (long long c = (long long)cta * nl + (lane - lane0); c < nchunks; c += (long long)p.pf_ctas * nl) {
+      const long long off = c * CH;
+      const long long left = p.pf_bytes[i] - off;
+      const uint32_t sz = (uint32_t)(left < CH ? left : CH);
+      if (sz >= 16u)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf[i] + off), "r"(sz) : "memory");
+    }
+  }
+}
+
 __device__ __forceinline__ void ln_row_stats(const GemmKParams& p, long long m, float& ln_r, float& ln_nm) {
   float s = 0.f, q = 0.f;
   const float2* base = p.ln_stats + m;
@@ -507,6 +531,8 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
     }
     if (p.nkb_extra > 0) tma_prefetch_desc(&tmAx);
   }
+  if (warp == W_TMA)   // lanes 2..31: the group's L2 prefetch hint, shared by the group's first CTAs
+    l2_prefetch_hint(p, (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * zsplit)), lane, 2);
   if (warp == W_TMA && lane == 1) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -1061,22 +1087,12 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   // (group 0), each tile re-binds `p` / the tensor maps to its own group
   const GemmKParams& p = L.g[0].p;
   const int num_tiles = tiles_per_group * (NG == 1 ? 1 : n_groups);
-  // Tile order.  Default: a CTA takes tiles blockIdx.x, + gridDim.x, ... with tm fastest (CTAs working side by side
-  // share their weight tile in L2).  LayerNorm-folded GEMMs: a CTA takes a CONTIGUOUS run of tiles with tn fastest, so
-  // consecutive tiles belong to the same rows and their LayerNorm statistics are reduced once per row block instead of
-  // once per tile (the per-tile reduction cost 6-21 us per launch, profiles/r02f_ln_consumer_cost.txt).
-  const bool row_major = p.ln_stats != nullptr;
-  const int n_tiles = tiles_per_group / m_tiles;
-  const int t_begin = row_major ? (int)((long long)blockIdx.x * num_tiles / gridDim.x) : (int)blockIdx.x;
-  const int t_end = row_major ? (int)((long long)(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
-  const int t_step = row_major ? 1 : (int)gridDim.x;
 #define EA_PERSIST_TILE_GROUP()                                                    \
   const int gi = NG == 1 ? 0 : tile / tiles_per_group;                             \
   const int gtile = NG == 1 ? tile : tile - gi * tiles_per_group;                  \
   const GemmGroup& GG = L.g[gi];                                                   \
   const GemmKParams& p = GG.p;                                                     \
-  const int tm = row_major ? gtile / n_tiles : gtile % m_tiles;                    \
-  const int tn = row_major ? gtile - tm * n_tiles : gtile / m_tiles;
+  const int tm = gtile % m_tiles, tn = gtile / m_tiles;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -1103,7 +1119,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
   const uint32_t acc_cols = tmem_cols_for(p.BN);
 
   if (warp == PW_TMA && lane == 0) {
-    const int g0 = NG == 1 ? 0 : min(t_begin / tiles_per_group, n_groups - 1);
+    const int g0 = NG == 1 ? 0 : min((int)blockIdx.x / tiles_per_group, n_groups - 1);
     tma_prefetch_desc(&L.g[g0].tmA0);
     tma_prefetch_desc(&L.g[g0].tmB);
     if (p.mode == EA_GEMM_CONV_S2 || p.mode == EA_GEMM_CONV_S2A) {
@@ -1112,6 +1128,9 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       tma_prefetch_desc(&L.g[g0].tmA3);
     }
     if (p.nkb_extra > 0) tma_prefetch_desc(&L.g[g0].tmAx);
+  }
+  if (warp == PW_TMA) {   // lanes 2..31: every group's L2 prefetch hint, shared by all CTAs of the launch
+    for (int g = 0; g < (NG == 1 ? 1 : n_groups); ++g) l2_prefetch_hint(L.g[g].p, (int)blockIdx.x, lane, 2);
   }
   if (warp == PW_TMA && lane == 1) {
     for (int s = 0; s < p.stages; ++s) {
@@ -1140,7 +1159,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       uint32_t phase = 0;
       uint8_t* sa = smem;
       const int cin = p.cin_blocks * BK;
-      for (int tile = t_begin; tile < t_end; tile += t_step) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         EA_PERSIST_TILE_GROUP()
         const CUtensorMap& tmA0 = GG.tmA0;
         const CUtensorMap& tmA1 = GG.tmA1;
@@ -1201,7 +1220,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     uint32_t phase = 0;
     int abuf = 0;
     uint32_t aphase = 0;
-    for (int tile = t_begin; tile < t_end; tile += t_step) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[abuf], aphase ^ 1u);      // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t td = tb + (uint32_t)abuf * acc_cols;
@@ -1243,9 +1262,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     constexpr int GSTEP = 64 * EPI_WG;   // column distance between two groups of one warp-group
     int abuf = 0, it = 0;
     uint32_t fphase = 0;
-    int ln_unit = -1;
-    float ln_r = 1.f, ln_nm = 0.f;
-    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       EA_PERSIST_TILE_GROUP()
       const bool has_res = p.residual != nullptr;
       const RowInfo ri = row_info(p, tm, r);
@@ -1256,12 +1273,8 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       uint4 rres[8];
       // LayerNorm fold, consumer side (see ea_gemm_kernel)
       const bool ln = p.ln_stats != nullptr;
-      if (ln && ln_unit != gi * m_tiles + tm) {   // row_major order: the same rows for n_tiles tiles in a row
-        ln_unit = gi * m_tiles + tm;
-        ln_r = 1.f;
-        ln_nm = 0.f;
-        if (ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
-      }
+      float ln_r = 1.f, ln_nm = 0.f;
+      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
       if (!geglu) {
         for (int i = et; i < p.BN; i += EPI_THREADS) {
           const int col = ncol0 + i;
@@ -1471,7 +1484,8 @@ static GemmPlan plan_gemm(int mt, int N, int nkb, int act, long long ws_floats, 
   // CTA pairs (cta_group::2): per SM the TMA stream per K-block shrinks from 16 KB + BN*128 B to
   // 16 KB + BN*64 B for the same 128 x BN MACs.  Only without split-K and for stride-1 shapes.
   // 64x64-level projections (M = 8192, N = K = 320: attention out / proj_out with residual): the model picks 96,
-  // the per-shape sweep (profiles/r02f_gemm_shape_sweep.txt) has 128 26 % faster.  EA_PL_N320_BN overrides for A/B.
+  // the per-shape sweep (profiles/r02f_gemm_shape_sweep.txt) has 128 26 % faster; in the step -0.03 ms (session 13).
+  // EA_PL_N320_BN overrides for A/B.
   static const int pl_n320_bn = (int)pl_env("EA_PL_N320_BN", 128.0);
   const int pin_bn = (mt == 64 && N == 320 && nkb == 5 && act != EA_ACT_GEGLU) ? pl_n320_bn : 0;
   if (allow_two && mt >= 2 && pin_bn == 0) {
@@ -1648,6 +1662,11 @@ static int gemm_fill_group(const ea_gemm_args* a, GemmGroup& G, GemmShape& sh) {
   p.out_scale = a->out_scale;
   p.accumulate = a->accumulate;
   p.row_scale = a->row_scale;
+  for (int i = 0; i < EA_GEMM_MAX_PREFETCH; ++i) {
+    p.pf[i] = reinterpret_cast<const char*>(a->prefetch[i]);
+    p.pf_bytes[i] = a->prefetch[i] ? (a->prefetch_bytes[i] & ~15LL) : 0;
+  }
+  p.pf_ctas = 0;   // set with the grid
   if (a->row_scale && (a->act == EA_ACT_GEGLU || a->rowstats_out || a->ln_stats)) return EA_ERR_ARG;
   sh.ln_any = a->rowstats_out || a->ln_stats;
   if (sh.ln_any) {
@@ -1871,6 +1890,14 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
     if (encode_2d(&L.g[g].tmB, ag->w, (uint64_t)sh0.Ktot, (uint64_t)ag->N, (uint64_t)ldw * 2, BK,
                   (uint32_t)(two ? BN / 2 : BN)))
       return EA_ERR_TMAP;
+  }
+  {   // L2 prefetch hints: how many CTAs share each group's range (the first ones to start)
+    const long long total_p = tiles * G;
+    const long long per_group = two ? (long long)((m_tiles + 1) / 2 * 2) * n_tiles : tiles * plan.splits;
+    const int share = sm_count() / G > 0 ? sm_count() / G : 1;
+    for (int g = 0; g < G; ++g)
+      L.g[g].p.pf_ctas = use_persist ? (int)(total_p < sm_count() ? total_p : sm_count())
+                                     : (int)(per_group < share ? per_group : share);
   }
   GemmLaunch<1> L1;
   if (G == 1) L1.g[0] = L.g[0];

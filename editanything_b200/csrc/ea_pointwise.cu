@@ -37,10 +37,21 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
                 int silu, int chunks, int ppc, int cached, int part_bytes, int phase,
                 float* __restrict__ ws) {
   pdl_launch_dependents();
-  pdl_wait();
   const int net = aff.ipg > 0 ? (int)blockIdx.y / aff.ipg : 0;
   const float* __restrict__ gamma = net == 0 ? aff.gamma[0] : net == 1 ? aff.gamma[1] : aff.gamma[2];
   const float* __restrict__ beta = net == 0 ? aff.beta[0] : net == 1 ? aff.beta[1] : aff.beta[2];
+  // the affine parameters are weights, not the previous kernel's output: fetch them before the dependency wait
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, ba = ga, bb = ga;
+  {
+    const int nvec0 = C >> 3, v0 = threadIdx.x % nvec0;
+    if ((int)threadIdx.x / nvec0 < (int)blockDim.x / nvec0) {
+      ga = __ldg(reinterpret_cast<const float4*>(gamma + (v0 << 3)));
+      gb = __ldg(reinterpret_cast<const float4*>(gamma + (v0 << 3) + 4));
+      ba = __ldg(reinterpret_cast<const float4*>(beta + (v0 << 3)));
+      bb = __ldg(reinterpret_cast<const float4*>(beta + (v0 << 3) + 4));
+    }
+  }
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   float* sh = reinterpret_cast<float*>(gn_smem);                  // [2*groups]
   float* part = reinterpret_cast<float*>(gn_smem + 512);          // [lanes][2][C] per-lane partials
@@ -75,7 +86,29 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
   if (active) {
+#ifndef EA_GN_NO_ASYNC
+    if (cached) {
+      // every pixel of this thread goes global -> shared memory asynchronously: all of its loads are in flight at
+      // once (ONE L2 round trip) instead of four at a time through registers (the launch was a chain of ~8 round trips
+      // for 11-15 us whatever the tensor size, profiles/r02c_launches.csv)
+      for (int pp = p0 + pl; pp < p1; pp += lanes) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&cache[(pp - p0) * nvec + v]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + ((long long)b * HW + pp) * lds) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 4
+      for (int pp = p0 + pl; pp < p1; pp += lanes) {
+        const uint4 u = cache[(pp - p0) * nvec + v];
+        float2 f0 = ea_unpack2(u.x), f1 = ea_unpack2(u.y), f2 = ea_unpack2(u.z), f3 = ea_unpack2(u.w);
+        float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cs[j] += vals[j]; cq[j] += vals[j] * vals[j]; }
+      }
+    } else
+#endif
+    {
+#pragma unroll 8
     for (int pp = p0 + pl; pp < p1; pp += lanes) {
       uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pp) * lds));
       if (cached) cache[(pp - p0) * nvec + v] = u;
@@ -83,6 +116,7 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
       float vals[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
       for (int j = 0; j < 8; ++j) { cs[j] += vals[j]; cq[j] += vals[j] * vals[j]; }
+    }
     }
     // per-(pixel lane, channel) partials -> shared memory (no atomics: 480 threads x 16 contended
     // shared atomics used to cost ~4 us per launch)
@@ -149,10 +183,6 @@ gn_fused_kernel(const ea_half* __restrict__ x, long long ldx, int C1,
     const float inv_n = 1.0f / ((float)HW * (float)cpg);
     float av[8], bv[8];
     {
-      float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-      float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c));
-      float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
       float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
       float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
       int gprev = -1;

@@ -6,6 +6,7 @@ utils/stable_diffusion_controlnet_inpaint.py:1607-1636 does with `self.controlne
 of libea_b200 launches (optionally replayed as a CUDA graph).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -293,8 +294,19 @@ class DenoiseEngine:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             lat0, xh0, c0 = self.lat.clone(), self.x_half.clone(), self.step_ctr.clone()
+            # the warm-up pass also records the step's GEMM sequence: in the captured pass every launch carries the
+            # next launch's weights as an L2 prefetch hint (ops.WeightLookahead; EA_WEIGHT_PREFETCH=0 turns it off,
+            # =2 looks two launches ahead)
+            dist = int(os.environ.get("EA_WEIGHT_PREFETCH", "1"))
+            mk = getattr(self.ops, "WeightLookahead", None)
+            single = self.runner.lockstep or not self.runner.cns     # launch order = execution order
+            la = mk(dist) if (mk is not None and dist > 0 and single) else None
             with torch.cuda.stream(s):
-                self._step_body()
+                if la is not None:
+                    with self.ops.weight_lookahead(la):
+                        self._step_body()
+                else:
+                    self._step_body()
             torch.cuda.current_stream().wait_stream(s)
             self.lat.copy_(lat0)
             self.x_half.copy_(xh0)
@@ -302,7 +314,11 @@ class DenoiseEngine:
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launch_count()
             with torch.cuda.graph(g):
-                self._step_body()
+                if la is not None:
+                    with self.ops.weight_lookahead(la.replay()):
+                        self._step_body()
+                else:
+                    self._step_body()
             self.launches_per_step = self.ops.launch_count() - n0
             self._graph = g
             self.lat.copy_(lat0)

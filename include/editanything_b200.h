@@ -79,6 +79,7 @@ void ea_reset_launch_count(void);
  * Constraints: N % 8 == 0, K % 8 == 0, Cin % 64 == 0, all leading dims % 8 == 0,
  *              pointers 16-byte aligned.
  */
+#define EA_GEMM_MAX_PREFETCH 3
 typedef struct ea_gemm_args {
   int mode;
   int M, N, K;               /* K used by LINEAR only */
@@ -131,6 +132,11 @@ typedef struct ea_gemm_args {
                                 before residual / accumulate - the spatial `conditioning_scale` map of
                                 ControlNetModel2.forward (utils/stable_diffusion_controlnet.py:789-802), resized to
                                 the residual's resolution, as a factor of the zero-conv accumulation */
+  const void* prefetch[3];     /* optional L2 prefetch hints: up to EA_GEMM_MAX_PREFETCH ranges of device memory that a LATER */
+  long long prefetch_bytes[3]; /* launch will read (its weights) - the first CTAs of this launch issue
+                                  cp.async.bulk.prefetch.L2 over them while they work, so HBM streams the next layer's
+                                  weights into the 126 MB L2 behind this layer's math.  Never changes results.
+                                  NULL / 0 = unused slot. */
   void* workspace;           /* optional device scratch for split-K (small-M, weight-bound layers): */
   long long workspace_bytes; /* first 64 KB = int counters that MUST be zero before the first use
                                 (the kernel re-zeroes them), rest = fp32 partial tiles.  NULL => K
