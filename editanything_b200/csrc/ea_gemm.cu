@@ -154,23 +154,22 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // round trip per partial (10 for C = 320, 40 for C = 1280: 22 % of all stall samples of the GEGLU launch,
 // profiles/r02c_gemm_ncu_source_hot.txt).  The adds keep their fixed order, so the result stays deterministic.
 // L2 prefetch of a later launch's weights (ea_gemm_args.prefetch): lanes `lane0 .. 31` of one warp in each of the first
-// pf_ctas CTAs walk the range in 8 KB pieces.  Issued before the dependency wait - weights are never produced by a
+// pf_ctas CTAs walk the range line by line.  Issued before the dependency wait - weights are never produced by a
 // predecessor kernel - so HBM works on the next layer while this one computes from L2.
 __device__ __forceinline__ void l2_prefetch_hint(const GemmKParams& p, int cta, int lane, int lane0) {
   if (cta >= p.pf_ctas || lane < lane0) return;
-  constexpr long long CH = 8192;
+  // One 128-byte line per instruction through the load/store path (prefetch.global.L2).  NOT cp.async.bulk.prefetch:
+  // bulk prefetches queue in the SM's TMA unit in front of the launch's own operand loads (measured +0.05..0.18 ms per
+  // step, profiles/r02g_weight_prefetch_ab.txt).
   const int nl = 32 - lane0;
 #pragma unroll 1
   for (int i = 0; i < EA_GEMM_MAX_PREFETCH; ++i) {
     if (p.pf[i] == nullptr) continue;
-    const long long nchunks = (p.pf_bytes[i] + CH - 1) / CH;
-    for (long long c = (long long)cta * nl + (lane - lane0); c < nchunks; c += (long long)p.pf_ctas * nl) {
-      const long long off = c * CH;
-      const long long left = p.pf_bytes[i] - off;
-      const uint32_t sz = (uint32_t)(left < CH ? left : CH);
-      if (sz >= 16u)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf[i] + off), "r"(sz) : "memory");
-    }
+    const long long nlines = p.pf_bytes[i] >> 7;
+    const char* base = p.pf[i];
+#pragma unroll 4
+    for (long long c = (long long)cta * nl + (lane - lane0); c < nlines; c += (long long)p.pf_ctas * nl)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (c << 7)));
   }
 }
 

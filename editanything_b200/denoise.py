@@ -300,7 +300,7 @@ class DenoiseEngine:
             dist = int(os.environ.get("EA_WEIGHT_PREFETCH", "1"))
             mk = getattr(self.ops, "WeightLookahead", None)
             single = self.runner.lockstep or not self.runner.cns     # launch order = execution order
-            la = mk(dist) if (mk is not None and dist > 0 and single) else None
+            la = mk(dist, int(os.environ.get("EA_WEIGHT_PREFETCH_MAXM", "512"))) if (mk is not None and dist > 0 and single) else None
             with torch.cuda.stream(s):
                 if la is not None:
                     with self.ops.weight_lookahead(la):

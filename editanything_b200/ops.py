@@ -132,8 +132,9 @@ class WeightLookahead:
     chain of short launches; weight-bound layers (8x8 / 16x16 latents, M = 128 / 512) then start from L2."""
     MIN_BYTES = 1 << 20      # smaller operands arrive within the launch's own first wave anyway
 
-    def __init__(self, distance=1):
-        self.distance, self.seq, self.mode, self.idx = distance, [], "record", 0
+    def __init__(self, distance=1, max_m=1 << 30):
+        self.distance, self.seq, self.mode, self.idx, self.max_m = distance, [], "record", 0, max_m   # max_m: only for
+        # launches with at most that many rows (weight-bound layers)
 
     def replay(self):
         self.mode, self.idx = "replay", 0
@@ -141,12 +142,12 @@ class WeightLookahead:
 
     def visit(self, gs, ws):
         if self.mode == "record":
-            self.seq.append([(w.data_ptr(), w.numel() * w.element_size()) for w in ws])
+            self.seq.append([(w.data_ptr(), w.numel() * w.element_size(), int(g.M)) for g, w in zip(gs, ws)])
             return
         n = len(self.seq)
         if n == 0:
             return
-        tgt = [t for t in self.seq[(self.idx + self.distance) % n] if t[1] >= self.MIN_BYTES]
+        tgt = [t[:2] for t in self.seq[(self.idx + self.distance) % n] if t[1] >= self.MIN_BYTES and t[2] <= self.max_m]
         self.idx += 1
         slots = [(g, k) for k in range(3) for g in gs]          # spread the ranges over the groups' slots
         for (ptr, nbytes), (g, k) in zip(tgt, slots):
