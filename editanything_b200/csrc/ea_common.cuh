@@ -120,6 +120,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same with an L2 eviction-priority hint (createpolicy encodings: 0x12F0000000000000 = evict first,
+// 0x14F0000000000000 = evict last); policy 0 = plain load.
+__device__ __forceinline__ void tma_load_2d_hint(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
+                                                 int c1, uint64_t policy) {
+  if (policy == 0ull) {
+    tma_load_2d(smem, m, bar, c0, c1);
+    return;
+  }
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0,
                                             int c1, int c2) {
   asm volatile(

@@ -78,6 +78,7 @@ struct GemmKParams {
   const char* pf[EA_GEMM_MAX_PREFETCH];   // L2 prefetch hints (a later launch's weights) or null; pf_ctas CTAs share each range
   long long pf_bytes[EA_GEMM_MAX_PREFETCH];
   int pf_ctas;
+  unsigned long long b_policy;   // L2 eviction hint of the W operand's TMA loads (0 = none)
   int dbg_id;  // experiment builds (-DEA_GEMM_TIMING): launch ordinal for the chain stamps
 };
 
@@ -584,7 +585,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
             tma_load_2d_2cta(sa + a_bytes, &tmB, full0 + 8u * stage, kb * BK, bcol);
           } else {
             tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, arow);
-            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+            tma_load_2d_hint(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol, p.b_policy);
           }
           EA_GT(kb - kb0, 1);
           sa += stage_bytes;
@@ -622,7 +623,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
             const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
             tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
           }
-          if (!TWO) tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+          if (!TWO) tma_load_2d_hint(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol, p.b_policy);
           c0 += BK;
           if (c0 == cin) { c0 = 0; if (++kw == 3) { kw = 0; ++kh; } }
           sa += stage_bytes;
@@ -1173,7 +1174,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, arow);
-            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+            tma_load_2d_hint(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol, p.b_policy);
             sa += stage_bytes;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; sa = smem; }
           }
@@ -1198,7 +1199,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
               const CUtensorMap* m = sel == 0 ? &tmA0 : sel == 1 ? &tmA1 : sel == 2 ? &tmA2 : &tmA3;
               tma_load_4d(sa, m, &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
             }
-            tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol);
+            tma_load_2d_hint(sa + a_bytes, &tmB, &full_bar[stage], kb * BK, bcol, p.b_policy);
             c0 += BK;
             if (c0 == cin) { c0 = 0; if (++kw == 3) { kw = 0; ++kh; } }
             sa += stage_bytes;
@@ -1666,6 +1667,10 @@ static int gemm_fill_group(const ea_gemm_args* a, GemmGroup& G, GemmShape& sh) {
     p.pf_bytes[i] = a->prefetch[i] ? (a->prefetch_bytes[i] & ~15LL) : 0;
   }
   p.pf_ctas = 0;   // set with the grid
+  // W operand: streamed once per step (3.16 GB through a 126 MB L2) - marked evict-first so that it displaces itself
+  // rather than the activations and skip tensors the following launches read.  EA_GEMM_W_EVICT=0 turns the hint off.
+  static const int w_evict = (int)pl_env("EA_GEMM_W_EVICT", 1.0);
+  p.b_policy = w_evict == 1 ? 0x12F0000000000000ull : w_evict == 2 ? 0x14F0000000000000ull : 0ull;
   if (a->row_scale && (a->act == EA_ACT_GEGLU || a->rowstats_out || a->ln_stats)) return EA_ERR_ARG;
   sh.ln_any = a->rowstats_out || a->ln_stats;
   if (sh.ln_any) {

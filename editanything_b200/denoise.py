@@ -294,10 +294,10 @@ class DenoiseEngine:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             lat0, xh0, c0 = self.lat.clone(), self.x_half.clone(), self.step_ctr.clone()
-            # the warm-up pass also records the step's GEMM sequence: in the captured pass every launch carries the
-            # next launch's weights as an L2 prefetch hint (ops.WeightLookahead; EA_WEIGHT_PREFETCH=0 turns it off,
-            # =2 looks two launches ahead)
-            dist = int(os.environ.get("EA_WEIGHT_PREFETCH", "1"))
+            # opt-in experiment (EA_WEIGHT_PREFETCH = look-ahead distance, default 0 = off): the warm-up pass records
+            # the step's GEMM sequence and in the captured pass every launch carries a later launch's weights as an L2
+            # prefetch hint (ops.WeightLookahead).  Measured SLOWER in every form (profiles/r02g_weight_prefetch_ab.txt)
+            dist = int(os.environ.get("EA_WEIGHT_PREFETCH", "0"))
             mk = getattr(self.ops, "WeightLookahead", None)
             single = self.runner.lockstep or not self.runner.cns     # launch order = execution order
             la = mk(dist, int(os.environ.get("EA_WEIGHT_PREFETCH_MAXM", "512"))) if (mk is not None and dist > 0 and single) else None
