@@ -465,7 +465,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(sample_steps=1)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def _oracle_step_fn(cfg):
@@ -607,10 +607,16 @@ def run_reference(args, rank, world):
                                    ("the reference's own cldm modules (oracle/_ref)" if kind == "reference" else "oracle port")},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): anything a library prints on the way (the reference's modules announce
+    # a missing xformers at import) goes to stderr
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -45,7 +45,9 @@ def load():
                             "pytorch_lightning.utilities.distributed": pld})
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    import cldm.cldm as C
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the reference prints at import ("No module 'xformers' ..."):
+        import cldm.cldm as C                       # keep stdout clean for bench.py's one JSON line
     return C
 
 
