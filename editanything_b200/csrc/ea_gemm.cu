@@ -1262,34 +1262,6 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
     constexpr int GSTEP = 64 * EPI_WG;   // column distance between two groups of one warp-group
     int abuf = 0, it = 0;
     uint32_t fphase = 0;
-    // The tile's column vectors (bias, time-embedding rows of its first / last image, LayerNorm-fold g) are fetched ONE
-    // TILE AHEAD into registers (each thread owns <= SV columns): their global-load latency used to open every tile's
-    // serial chain (loads -> shared memory -> barrier -> TMEM drain).  Raw values are kept; sums happen at store time.
-    constexpr int SV = 256 / EPI_THREADS > 0 ? 256 / EPI_THREADS : 1;
-    float sv_b[SV], sv_r0[SV], sv_r1[SV];
-    auto side_load = [&](const int tile) {
-      EA_PERSIST_TILE_GROUP()
-      const int ncol0 = tn * p.BN;
-      const bool ln = p.ln_stats != nullptr;
-      const bool gg = p.act == EA_ACT_GEGLU;
-      const int bf = gg ? 0 : row_info(p, tm, 0).batch, bl = gg ? 0 : row_info(p, tm, BM - 1).batch;
-#pragma unroll
-      for (int k = 0; k < SV; ++k) {
-        const int i = et + k * EPI_THREADS;
-        const int col = ncol0 + i;
-        const bool in = i < p.BN && col < p.N;
-        sv_b[k] = (in && p.bias) ? __ldg(p.bias + col) : 0.f;
-        if (gg) {
-          sv_r0[k] = 0.f;
-          sv_r1[k] = (in && ln) ? __ldg(p.ln_g + col) : 0.f;
-        } else {
-          sv_r0[k] = (in && p.rowvec) ? __ldg(p.rowvec + (long long)bf * p.rowvec_ld + col) : 0.f;
-          sv_r1[k] = !in ? 0.f : ln ? __ldg(p.ln_g + col)
-                                    : (p.rowvec ? __ldg(p.rowvec + (long long)bl * p.rowvec_ld + col) : 0.f);
-        }
-      }
-    };
-    if ((int)blockIdx.x < num_tiles) side_load(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       EA_PERSIST_TILE_GROUP()
       const bool has_res = p.residual != nullptr;
@@ -1297,28 +1269,34 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
       const int ncol0 = tn * p.BN;
       float* cbt = cb + (it & 1) * 512;
       const long long lin_m0 = p.mode == EA_GEMM_LINEAR ? (long long)tm * BM + wq * 32 : -1;
-      const int b_first = row_info(p, tm, 0).batch;
+      const int b_first = row_info(p, tm, 0).batch, b_last = row_info(p, tm, BM - 1).batch;
       uint4 rres[8];
       // LayerNorm fold, consumer side (see ea_gemm_kernel)
       const bool ln = p.ln_stats != nullptr;
       float ln_r = 1.f, ln_nm = 0.f;
-      if (!geglu && has_res && wg * 64 < p.BN)
-        residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
-#pragma unroll
-      for (int k = 0; k < SV; ++k) {
-        const int i = et + k * EPI_THREADS;
-        if (i < p.BN) {
-          if (geglu) {
-            cbt[i] = sv_b[k];
-            if (ln) cbt[256 + i] = sv_r1[k];
-          } else {
-            cbt[i] = sv_b[k] + sv_r0[k];
-            cbt[256 + i] = ln ? sv_r1[k] : sv_b[k] + sv_r1[k];
+      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
+      if (!geglu) {
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
+          const int col = ncol0 + i;
+          float v0 = 0.f, v1 = 0.f;
+          if (col < p.N) {
+            const float bsum = p.bias ? __ldg(p.bias + col) : 0.f;
+            v0 = bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_first * p.rowvec_ld + col) : 0.f);
+            v1 = ln ? __ldg(p.ln_g + col)
+                    : bsum + (p.rowvec ? __ldg(p.rowvec + (long long)b_last * p.rowvec_ld + col) : 0.f);
           }
+          cbt[i] = v0;
+          cbt[256 + i] = v1;
+        }
+        if (has_res && wg * 64 < p.BN)
+          residual_load64(rres, p.residual, p.ldr, lane, ri.m, ri.ok, ncol0 + wg * 64, p.BN - wg * 64, p.N, lin_m0, p.M);
+      } else {
+        for (int i = et; i < p.BN; i += EPI_THREADS) {
+          const bool in = ncol0 + i < p.N;
+          cbt[i] = (p.bias && in) ? __ldg(p.bias + ncol0 + i) : 0.f;
+          if (ln) cbt[256 + i] = in ? __ldg(p.ln_g + ncol0 + i) : 0.f;
         }
       }
-      if (tile + (int)gridDim.x < num_tiles) side_load(tile + gridDim.x);   // in flight behind this tile's work
-      if (ln && ri.ok) ln_row_stats(p, ri.m, ln_r, ln_nm);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull_bar[abuf], fphase);
       tc_fence_after();
