@@ -1045,8 +1045,9 @@ static void conv_geometry(int H, int W, int& bw, int& bh, int& bn) {
 }
 
 // ---- persistent variant ---------------------------------------------------------------------------
-// EXPERIMENTAL (off unless ea_gemm_args.force_persistent = 1 or EA_GEMM_PERSIST=1; not yet validated on
-// hardware - DESIGN.md section 8, item 1).  One CTA per SM walks the tile list (tile -> (tm, tn) with tm
+// The DEFAULT kernel for every launch without split-K / CTA pairs (the 8-warp form; EA_GEMM_PERSIST=0|1|2 and
+// ea_gemm_args.force_persistent override; validated bit-for-bit against the one-tile kernel by
+// tests/test_gpu_gemm_persistent.py).  One CTA per SM walks the tile list (tile -> (tm, tn) with tm
 // fastest, so CTAs working side by side share their weight tile in L2) with TWO TMEM accumulators: the
 // epilogue warps drain tile i while the MMA warp already accumulates tile i+1, the TMA ring runs across
 // tile boundaries, and barrier setup / TMEM allocation / the dependency wait are paid once per SM instead
@@ -1895,6 +1896,11 @@ extern "C" int ea_gemm_grouped(const ea_gemm_args* args, int n_groups, void* str
                   (uint32_t)(two ? BN / 2 : BN)))
       return EA_ERR_TMAP;
   }
+  // The evict-first hint on W pays where a weight tile is used within about one wave (<= 64 row tiles per network: the
+  // step at 1 image / GPU, SAM).  With thousands of row tiles (VAE: M up to 262144; 4 images / GPU at 64x64) the same
+  // weight tile is re-read wave after wave and the hint cost 0.4-4 % (round 2, session 22): plain loads there.
+  if (m_tiles > 64)
+    for (int g = 0; g < G; ++g) L.g[g].p.b_policy = 0ull;
   {   // L2 prefetch hints: how many CTAs share each group's range (the first ones to start)
     const long long total_p = tiles * G;
     const long long per_group = two ? (long long)((m_tiles + 1) / 2 * 2) * n_tiles : tiles * plan.splits;
