@@ -379,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
         hh = [h.pin_memory() for h in hints]
         himg = torch.randn(1, 3, 1024, 1024).pin_memory() if sam is not None else None
         hsrc = (torch.rand(1, 3, 512, 512) * 2 - 1).pin_memory() if vae is not None else None
-        n_rep = 3
+        n_rep = 5
         from editanything_b200.sharding import gather_sharded
 
         def one_pass():
@@ -404,15 +404,27 @@ def run_ours(args, rank, world, local_rank):
                     torch.cat(_all_gather_list(res, world))          # the single end-of-job collective
             return res.cpu(), emb
 
+        import gc
+        one_pass()
         one_pass()
         torch.cuda.synchronize()
+        # the timed passes run with the cyclic garbage collector parked, as a serving process would (gc.freeze() after
+        # start-up): a generation-2 collection over the imported module graph is a 50-200 ms host stall that landed in
+        # some runs' timed region and not in others (e2e 362 vs 417-437 ms / image at the same device time)
+        gc.collect()
+        gc.freeze()
+        gc.disable()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        pass_ms = []
         for _ in range(n_rep):
-            res, emb = one_pass()
+            tp = time.perf_counter()
+            res, emb = one_pass()          # ends with a D2H copy of the result: the pass is complete when it returns
+            pass_ms.append(round((time.perf_counter() - tp) * 1e3, 1))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        gc.enable()
         if world > 1:
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -424,11 +436,12 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": round(world * n_img * n_rep / dt, 4), "unit": "images/s",
                "h2d_bytes_per_step": h2d // DDIM_STEPS, "d2h_bytes_per_step": d2h // DDIM_STEPS,
                "ms_per_image": round(dt / (n_rep * n_img) * 1e3, 2), "images_timed": n_rep * n_img,
+               "pass_ms": pass_ms,
                "note": "per image: pinned host image -> H2D -> SAM ViT-H encode -> D2H embedding; pinned host source "
                        "image -> H2D -> VAE encode; pinned host ctx / hints / noise -> H2D -> prepare (ctx K/V, hint "
                        "stacks) -> 50 fused steps (one graph launch per step) -> VAE decode -> uint8 tiles -> "
-                       "(N > 1: one NCCL all-gather of all ranks' tiles, inside the timed region) -> D2H; 1 untimed "
-                       "warm-up pass; text encoder / SAM mask decoder not included (SURVEY.md 8f)"}
+                       "(N > 1: one NCCL all-gather of all ranks' tiles, inside the timed region) -> D2H; 2 untimed "
+                       "warm-up passes, garbage collector parked; text encoder / SAM mask decoder not included (SURVEY.md 8f)"}
 
     line = {
         "metric": "512x512 50-step SAM+ControlNet-inpaint images/sec; fused ControlNetx2+UNet+CFG+DDIM step ms",
