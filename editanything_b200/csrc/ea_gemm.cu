@@ -746,7 +746,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
     if (fast) {
       const float* cbr = cb + ((!ln && ri.batch != b_first) ? 256 : 0);
       // one 32-column chunk: residual hand-off, bias / activation / scale / residual, staging, flush
-      auto process = [&](const uint32_t (&v)[32], const int c) {
+      auto process = [&](uint32_t (&v)[32], const int c) {
         const int n_first = ncol0 + c;
         const int half = (c >> 5) & 1;
         if (has_res && half == 0) {
@@ -784,6 +784,10 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
               f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
             }
           }
+#ifndef EA_EPI_TWO_BUFFERS
+          // v is dead from here on: the next chunk's tcgen05.ld reuses its registers (see the persistent kernel)
+          if (c + 32 < p.BN) tmem_ld32(taddr + (uint32_t)(c + 32), v);
+#endif
           if (p.act == EA_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_SILU);
@@ -825,6 +829,7 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
       // TMEM loads are double-buffered: the next chunk's tcgen05.ld is in flight while this chunk is
       // converted and stored (one warp per SM sub-partition: nothing else hides the load latency)
       // (one copy of the chunk body: vb is moved into va instead of instantiating `process` twice)
+#ifdef EA_EPI_TWO_BUFFERS
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, vb);
       for (int c = 0; c < p.BN; c += 32) {
@@ -834,6 +839,14 @@ ea_gemm_kernel(const __grid_constant__ GemmLaunch<NG> L) {
         if (c + 32 < p.BN) tmem_ld32(taddr + (uint32_t)(c + 32), vb);
         process(va, c);
       }
+#else
+      uint32_t va[32];
+      tmem_ld32(taddr, va);
+      for (int c = 0; c < p.BN; c += 32) {
+        tmem_ld_wait();
+        process(va, c);
+      }
+#endif
     } else
     if (p.splits == 1) {
       if (geglu) {
@@ -1310,7 +1323,7 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
         // instruction body, which no longer fit the 32 KB L1.5 instruction cache - measured +0.25 ms per step
         // (profiles/r02e_ab_epilogue.txt).
         auto next_chunk = [&](int c) { return ((c & 32) == 0 && c + 32 < p.BN) ? c + 32 : (c & ~63) + GSTEP; };
-        auto process = [&](const uint32_t (&v)[32], const int c) {
+        auto process = [&](uint32_t (&v)[32], const int c, const int nc) {
           const int n_first = ncol0 + c;
           const int half = (c >> 5) & 1;
           if (has_res && half == 0) {
@@ -1346,6 +1359,11 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
                 f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
               }
             }
+#ifndef EA_EPI_TWO_BUFFERS
+            // v is dead from here on: the next chunk's tcgen05.ld goes into the SAME registers and is in flight behind
+            // the activation / pack / staging / flush below - no second buffer, no 32 register moves per chunk
+            if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, v);
+#endif
             if (p.act == EA_ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = act_call(f[j], EA_ACT_SILU);
@@ -1383,8 +1401,9 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
             stage_flush(stg, lane, p.out, p.ldo, p.out2, p.ldo2, ri.m, ri.ok, n_first - half * 32,
                         half == 1 ? 8 : 4, p.N, lin_m0, p.M);
         };
-        uint32_t va[32], vb[32];
         int c = wg * 64;
+#ifdef EA_EPI_TWO_BUFFERS   // A/B: the previous form (second register buffer, copied per chunk)
+        uint32_t va[32], vb[32];
         if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, vb);
         while (c < p.BN) {
           tmem_ld_wait();
@@ -1392,9 +1411,19 @@ ea_gemm_persistent_kernel(const __grid_constant__ GemmLaunch<NG> L, const int ti
           for (int j = 0; j < 32; ++j) va[j] = vb[j];
           const int nc = next_chunk(c);
           if (nc < p.BN) tmem_ld32(taddr + (uint32_t)nc, vb);
-          process(va, c);
+          process(va, c, nc);
           c = nc;
         }
+#else
+        uint32_t va[32];
+        if (c < p.BN) tmem_ld32(taddr + (uint32_t)c, va);
+        while (c < p.BN) {
+          tmem_ld_wait();
+          const int nc = next_chunk(c);
+          process(va, c, nc);
+          c = nc;
+        }
+#endif
       } else if (EPI_WG == 1) {
         for (int c = 0; c < half_bn; c += 32) {
           uint32_t xv[32], gv[32];

@@ -18,6 +18,21 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
 
 
+def test_nothing_is_exported_that_the_header_does_not_declare():
+    """The reverse direction: no undeclared `ea_*` entry point (debug hooks exist only in -DEA_GEMM_TIMING builds)."""
+    import shutil
+    import subprocess
+    nm = shutil.which("nm")
+    if nm is None:
+        import pytest
+        pytest.skip("binutils nm not available")
+    out = subprocess.run([nm, "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("ea_")}
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "editanything_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(ea_[a-z0-9_]+)\s*\(", hdr))
+    assert exported <= declared, exported - declared
+
+
 def test_library_reports_dtype_and_errors_without_gpu():
     lib = _lib.load()
     assert lib.ea_version() >= 1
