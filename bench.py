@@ -629,6 +629,12 @@ _JSON_OUT = sys.stdout
 def main():
     # stdout carries exactly ONE line (the JSON): anything a library prints on the way (the reference's modules announce
     # a missing xformers at import) goes to stderr
+    # ... including what C libraries write to file descriptor 1 (NCCL announces its version there): fd 1 is pointed at
+    # stderr and the JSON line goes to a duplicate of the original stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
