@@ -7,20 +7,23 @@
 //     ResBlock's 1x1 skip convolution folded in as extra K-blocks (openaimodel.py:233-240,274)
 //   * 3x3 stride-2 pad-1 convolutions (Downsample, openaimodel.py:133-159) (mode CONV_S2)
 //
-// Structure (one 128 x BN output tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the
-// other's main loop):
-//   warp 0     TMA producer : A tile (128 rows x 64 halves, SWIZZLE_128B) and B tile (BN x 64)
-//                             into a `stages`-deep shared-memory ring, mbarrier-signalled.
-//                             For convolutions the A tile of filter tap (kh,kw) is a 4-D box
-//                             {64ch, bw, bh, bn} of the NHWC tensor shifted by (kh-1, kw-1); the
-//                             zero padding is TMA out-of-bounds fill, no im2col buffer exists.
-//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per
-//                             stage, accumulating fp32 in TMEM; tcgen05.commit releases stages.
-//   warp 2     TMEM allocator
-//   warps 4-7  epilogue     : tcgen05.ld the accumulator (thread <-> row), fused
-//                             bias / time-embedding row vector / SiLU|GELU|GEGLU / scale /
-//                             residual add / accumulate-into-destination (ControlNet zero-conv
-//                             residual, cldm/cldm.py:34-41) / dual store, 16-byte stores.
+// Two kernels share the main loop and the fused epilogue:
+//   * ea_gemm_persistent_kernel (default when K is not split): ONE CTA per SM walks the tile list with two TMEM
+//     accumulators - eight epilogue warps drain tile i while the MMA warp accumulates tile i + 1 (the overlap a second
+//     co-resident CTA would give; with 150-200 KB of shared memory per CTA a second one never fits, ncu: 1 block / SM).
+//   * ea_gemm_kernel (one 128 x BN tile per CTA): split-K and CTA-pair (cta_group::2) launches of the small-M,
+//     weight-bound layers; up to 2 CTAs per SM when the stage ring is shallow enough (the planner's `occ`).
+// Roles in both:
+//   TMA producer : A tile (128 rows x 64 halves, SWIZZLE_128B) and B tile (BN x 64) into a `stages`-deep shared-memory
+//                  ring, mbarrier-signalled.  For convolutions the A tile of filter tap (kh,kw) is a 4-D box
+//                  {64ch, bw, bh, bn} of the NHWC tensor shifted by (kh-1, kw-1); the zero padding is TMA out-of-bounds
+//                  fill, no im2col buffer exists.  W-operand loads carry an L2 evict-first hint (see gemm_fill_group).
+//   MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage, accumulating fp32 in TMEM;
+//                  tcgen05.commit releases stages.  Also allocates TMEM.
+//   epilogue     : tcgen05.ld the accumulator (thread <-> row) into ONE 32-register buffer that is reloaded as soon as
+//                  it has been converted; fused bias / time-embedding row vector / LayerNorm fold / SiLU|GELU|GEGLU /
+//                  scale / residual add / accumulate-into-destination (ControlNet zero-conv residual,
+//                  cldm/cldm.py:34-41) / dual store, rows written as coalesced 128-byte pieces through shared memory.
 #include "ea_common.cuh"
 #include "ea_internal.h"
 
